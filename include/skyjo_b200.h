@@ -1,0 +1,203 @@
+/*
+ * skyjo_b200.h -- C ABI of libskyjo_b200.so, the B200-native batched SkyJo environment.
+ *
+ * The reference (michaelfeil/skyjo_rl) has no FFI: its boundary is two Python classes,
+ * `SkyjoGame` (rlskyjo/game/skyjo.py:19) and the PettingZoo env `SimpleSkyjoEnv`
+ * (rlskyjo/environment/skyjo_env.py:29).  This header is the boundary a replacement
+ * binds instead; each entry point names the reference interface it replaces.  The Python
+ * host (skyjo_rl_b200/env.py) loads it with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only; every *_dev pointer is a CUDA device pointer owned by the caller
+ *     (torch tensors' data_ptr()), every *_host pointer is host memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are
+ *     asynchronous on it unless the comment says "synchronises";
+ *   - return value 0 = success, otherwise an SKYJO_E_* code (or 1000 + cudaError_t);
+ *     the message is available from skyjo_last_error() (thread-local);
+ *   - illegal actions are data, not errors: the env terminates with reward -1 for the
+ *     offender (TerminateIllegalWrapper semantics, skyjo_env.py:23).
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef SKYJO_B200_H
+#define SKYJO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKYJO_ABI_VERSION 1
+#define SKYJO_MAX_PLAYERS 12
+#define SKYJO_NUM_ACTIONS 26 /* skyjo.py:46 action_mask_shape */
+#define SKYJO_DECK 150       /* skyjo.py:80 */
+#define SKYJO_NUM_STATS 32
+
+enum {
+    SKYJO_OK = 0,
+    SKYJO_E_INVALID = 1,    /* bad argument / config (skyjo.py:24-26 assert) */
+    SKYJO_E_NOT_BOUND = 2,  /* outputs not bound */
+    SKYJO_E_STATE = 3,      /* device-side consistency flag raised (see skyjo_check) */
+    SKYJO_E_NO_DEVICE = 4,
+    SKYJO_E_CUDA = 1000     /* + cudaError_t */
+};
+
+/* action tensor element types accepted by skyjo_step */
+enum { SKYJO_ACT_U8 = 0, SKYJO_ACT_I8 = 1, SKYJO_ACT_I32 = 2, SKYJO_ACT_I64 = 3 };
+
+/* values of the per-env `done` byte written by every step */
+enum {
+    SKYJO_RUNNING = 0,
+    SKYJO_DONE_GAME_OVER = 1, /* skyjo.py:350-356 */
+    SKYJO_DONE_ILLEGAL = 2,   /* skyjo_env.py:23 */
+    SKYJO_DONE_TRUNCATED = 3  /* step cap (vanilla_env_example.py:14 uses 300*N) */
+};
+
+/* indices into the statistics vector (int64[SKYJO_NUM_STATS]) */
+enum {
+    SKYJO_STAT_EPISODES = 0,          /* games that reached game over */
+    SKYJO_STAT_EPISODE_STEPS = 1,     /* sum of their lengths in act() calls */
+    SKYJO_STAT_SCORE_RAW_SUM = 2,     /* sum over seats of the unpenalised score */
+    SKYJO_STAT_WINNER_RAW_SUM = 3,    /* sum of min-over-seats raw score */
+    SKYJO_STAT_FINISHER_RAW_SUM = 4,  /* sum of the finisher's raw score */
+    SKYJO_STAT_PENALISED = 5,         /* games whose finisher was penalised (skyjo.py:496) */
+    SKYJO_STAT_PENALISED_RAW_SUM = 6, /* sum of those finishers' raw scores */
+    SKYJO_STAT_REFUNDS = 7,           /* column removals in finished games (skyjo.py:419) */
+    SKYJO_STAT_RESHUFFLES = 8,        /* in-game draw-pile reshuffles (skyjo.py:361-365) */
+    SKYJO_STAT_ILLEGAL = 9,
+    SKYJO_STAT_TRUNCATED = 10,
+    SKYJO_STAT_ACT_DRAW_PILE = 11,    /* action 24 */
+    SKYJO_STAT_ACT_TAKE_DISCARD = 12, /* action 25 */
+    SKYJO_STAT_ACT_SWAP = 13,         /* actions 0..11 */
+    SKYJO_STAT_ACT_FLIP = 14,         /* actions 12..23 */
+    SKYJO_STAT_STARTER_SEAT0 = 15,    /* finished games started by seat 0 */
+    SKYJO_STAT_STEPS = 16,            /* all act() calls */
+    SKYJO_STAT_WINS_SEAT0 = 17        /* .. +11: first argmin of the final scores */
+};
+
+/* Mirrors the keyword arguments of SkyjoGame.__init__ (skyjo.py:20-22) and
+ * SimpleSkyjoEnv.__init__ (skyjo_env.py:38-45). */
+typedef struct SkyjoConfig {
+    int32_t num_players;                   /* 1..12 */
+    int32_t observe_other_player_indirect; /* 0: obs has 19+12N entries, 1: 31 */
+    double score_penalty;
+    double mean_reward;
+    double reward_refunded;
+    int32_t auto_reset;        /* 1: a finished env starts its next episode in the same step */
+    int32_t max_episode_steps; /* 0 = no truncation */
+} SkyjoConfig;
+
+/* Output buffers (device).  Shapes: obs int8[B, D]; action_mask int8[B, 26];
+ * agent int8[B] (= expected_action[0], agent_selection is "player_<agent>");
+ * done uint8[B]; reward float64[B, N]; final_score float64[B, N]. */
+typedef struct SkyjoOutputs {
+    void *obs_dev;
+    void *action_mask_dev;
+    void *agent_dev;
+    void *done_dev;
+    void *reward_dev;
+    void *final_score_dev;
+} SkyjoOutputs;
+
+/* SkyjoGame-shaped view of one env for debugging and parity tests
+ * (players_cards / players_masked / hand_card / expected_action / game_metrics). */
+typedef struct SkyjoEnvDebug {
+    int8_t players_cards[SKYJO_MAX_PLAYERS][12];  /* true values; -14 where refunded */
+    int8_t players_masked[SKYJO_MAX_PLAYERS][12]; /* 2 hidden, 1 open, 0 refunded */
+    int8_t discard_hist[16];  /* multiset of the discard pile: count of value j-2 in [j] */
+    int8_t draw_hist[16];     /* valid when draw_is_multiset */
+    int8_t drawpile[SKYJO_DECK]; /* python-list order (top = last), valid otherwise */
+    int16_t n_draw;
+    int16_t n_discard;
+    int8_t hand_card;    /* 15 = none (skyjo.py:33) */
+    int8_t discard_top;  /* -3 = empty (skyjo.py:254) */
+    int8_t expected_player;
+    int8_t expected_phase; /* 0 draw, 1 place */
+    int8_t starter;
+    int8_t is_terminated;
+    int8_t draw_is_multiset; /* 1 after an in-game reshuffle (DESIGN.md "reshuffle") */
+    int8_t n_reshuffles;
+    int32_t step_in_episode;
+    uint32_t episode;
+    int8_t num_refunded[SKYJO_MAX_PLAYERS];
+    int16_t num_placed[SKYJO_MAX_PLAYERS];
+    int8_t pad[8];
+} SkyjoEnvDebug;
+
+typedef struct SkyjoHandle SkyjoHandle;
+
+int skyjo_abi_version(void);
+const char *skyjo_last_error(void);
+
+/* skyjo.py:43-45 obs_shape */
+int skyjo_obs_len(const SkyjoConfig *cfg);
+/* bytes of device state the caller must allocate (256-byte aligned) for num_envs games */
+int64_t skyjo_state_bytes(const SkyjoConfig *cfg, int64_t num_envs);
+
+/* Replaces SkyjoGame.__init__ / SimpleSkyjoEnv.__init__ for a batch: env i of this handle
+ * is global env first_global_env_id + i; its RNG streams depend only on (seed, global id),
+ * so any sharding of a global batch over handles/GPUs plays identical games. */
+int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t seed,
+                 int64_t first_global_env_id, void *state_dev, int64_t state_bytes,
+                 SkyjoHandle **out);
+int skyjo_destroy(SkyjoHandle *h);
+int skyjo_bind_outputs(SkyjoHandle *h, const SkyjoOutputs *outs);
+
+/* SkyjoGame.reset (skyjo.py:52-74) / SimpleSkyjoEnv.reset (skyjo_env.py:254-267) for every
+ * env: Philox deck shuffle, deal, two flips per player, start player; writes obs / mask /
+ * agent for the first turn, zeroes done / reward. */
+int skyjo_reset(SkyjoHandle *h, void *stream);
+/* Same with the shuffles and flips injected: decks int8[B,150], flips
+ * uint8[B,N,2].  Decks must hold values -2..12, at most 15 copies of each. */
+int skyjo_reset_injected(SkyjoHandle *h, const int8_t *decks_dev, const uint8_t *flips_dev,
+                         void *stream);
+/* SimpleSkyjoEnv.seed (skyjo_env.py:280-290): new seed, episode counters to 0, then reset */
+int skyjo_seed(SkyjoHandle *h, uint64_t seed, void *stream);
+
+/* One fused launch per call = SimpleSkyjoEnv.step (skyjo_env.py:216-252) + observe
+ * (:199-214) for the next agent, for all envs: SkyjoGame.act (skyjo.py:308-335),
+ * _calc_final_rewards (skyjo_env.py:293-312), collect_observation (skyjo.py:148-199). */
+int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *stream);
+/* n_steps fused launches with the uniform legal policy (random_admissible_policy.py:26-28)
+ * drawn in-kernel: the loop of sample_game.py:10-21. */
+int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream);
+/* Host-buffer entry for end-to-end use: copies actions (uint8[B]) to the device, steps,
+ * copies obs / mask / agent / done / reward back; synchronises.  Null outputs are skipped. */
+int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host,
+                    int8_t *mask_host, int8_t *agent_host, uint8_t *done_host,
+                    double *reward_host, void *stream);
+
+/* SimpleSkyjoEnv.observe(agent) (skyjo_env.py:199-214) for an arbitrary seat; agent = -1
+ * means each env's agent_selection.  Writes int8[B,D] / int8[B,26]. */
+int skyjo_observe(SkyjoHandle *h, int agent, void *obs_dev, void *mask_dev, void *stream);
+
+/* Episode statistics (SkyjoGame.game_metrics aggregated, skyjo.py:56-60).  *_device reduces
+ * into int64[SKYJO_NUM_STATS] on the device (feed it to an NCCL all-reduce); *_host also
+ * copies to the host and synchronises. */
+int skyjo_stats_device(SkyjoHandle *h, int64_t *out_dev, void *stream);
+int skyjo_stats_host(SkyjoHandle *h, int64_t *out_host, void *stream);
+int skyjo_stats_clear(SkyjoHandle *h, void *stream);
+
+/* SkyjoGame-shaped dump of envs [env0, env0+count) into out_dev (device memory). */
+int skyjo_export_debug(SkyjoHandle *h, int64_t env0, int64_t count, SkyjoEnvDebug *out_dev,
+                       void *stream);
+/* Synchronises; returns SKYJO_E_STATE if a kernel raised the consistency flag. */
+int skyjo_check(SkyjoHandle *h, void *stream);
+/* lockstep counter (number of step launches since creation / seed) */
+int64_t skyjo_step_count(const SkyjoHandle *h);
+/* restore the lockstep counter when resuming from a saved state buffer */
+int skyjo_set_step_count(SkyjoHandle *h, int64_t t);
+/* kernels launched by this handle so far */
+int64_t skyjo_launch_count(const SkyjoHandle *h);
+
+/* Host twins of the device RNG streams, so a CPU checker can be dealt identical games. */
+void skyjo_host_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void skyjo_host_deck(uint64_t seed, uint64_t global_env, uint32_t episode, int8_t out[SKYJO_DECK]);
+void skyjo_host_flips(uint64_t seed, uint64_t global_env, uint32_t episode, int num_players,
+                      uint8_t *out /* [N][2] */);
+int skyjo_host_policy(uint64_t seed, uint64_t global_env, uint64_t t, uint32_t legal_bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKYJO_B200_H */

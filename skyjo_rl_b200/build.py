@@ -1,0 +1,66 @@
+"""In-tree build of libskyjo_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+
+    python -m skyjo_rl_b200.build [--force]
+
+The fused step kernel is instantiated once per player count (csrc/skyjo_step_inst.cu with
+-DSKYJO_N=1..12); the 13 translation units compile in parallel and link into
+skyjo_rl_b200/libskyjo_b200.so next to this file, so the library travels with the tree.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libskyjo_b200.so")
+NVCC = os.environ.get("NVCC", "nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--fmad=false",
+]
+
+
+def _sources():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "skyjo_b200.h")]
+    return deps
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(job):
+    src, obj, extra = job
+    cmd = [NVCC, *FLAGS, *extra, "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return obj
+
+
+def build(force=False, verbose=False):
+    deps = _sources()
+    if not force and not _stale(LIB, deps):
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(OBJ, "skyjo_capi.o"), [])]
+    for n in range(1, 13):
+        jobs.append((os.path.join(CSRC, "skyjo_step_inst.cu"), os.path.join(OBJ, f"skyjo_step_n{n}.o"), [f"-DSKYJO_N={n}"]))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(_compile, jobs))
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed: {r.stdout}\n{r.stderr}")
+    if verbose:
+        print("built", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

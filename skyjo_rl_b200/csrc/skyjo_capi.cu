@@ -1,0 +1,441 @@
+// skyjo_capi.cu -- the C ABI of libskyjo_b200.so (include/skyjo_b200.h): handle management,
+// launch scheduling of the deal / step / observe kernels, statistics, host RNG twins.
+// No torch, no CPU fallback: every compute entry launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/skyjo_b200.h"
+#include "skyjo_deal.cuh"
+#include "skyjo_rng.cuh"
+#include "skyjo_state.cuh"
+#include "skyjo_step.cuh"
+
+namespace skyjo {
+#define SKYJO_DECL(n)                                                                                     \
+    cudaError_t launch_step_##n(const StepParams &, bool, bool, cudaStream_t);                            \
+    cudaError_t launch_observe_##n(const StepParams &, bool, int, int8_t *, int8_t *, int, int, cudaStream_t);
+SKYJO_DECL(1) SKYJO_DECL(2) SKYJO_DECL(3) SKYJO_DECL(4) SKYJO_DECL(5) SKYJO_DECL(6)
+SKYJO_DECL(7) SKYJO_DECL(8) SKYJO_DECL(9) SKYJO_DECL(10) SKYJO_DECL(11) SKYJO_DECL(12)
+#undef SKYJO_DECL
+
+static const step_launch_fn kStep[SKYJO_MAX_PLAYERS] = {
+    launch_step_1, launch_step_2, launch_step_3, launch_step_4,  launch_step_5,  launch_step_6,
+    launch_step_7, launch_step_8, launch_step_9, launch_step_10, launch_step_11, launch_step_12};
+static const observe_launch_fn kObserve[SKYJO_MAX_PLAYERS] = {
+    launch_observe_1, launch_observe_2, launch_observe_3, launch_observe_4,  launch_observe_5,  launch_observe_6,
+    launch_observe_7, launch_observe_8, launch_observe_9, launch_observe_10, launch_observe_11, launch_observe_12};
+}  // namespace skyjo
+
+using namespace skyjo;
+
+struct SkyjoHandle {
+    SkyjoConfig cfg;
+    int device;
+    long long B, Bpad;
+    unsigned long long seed, first_env;
+    DeviceState st;
+    long long *stats_tmp;  // device int64[NUM_STATS]
+    SkyjoOutputs outs;
+    bool bound;
+    int bulk_ok;
+    unsigned long long t;   // lockstep counter
+    long long launches;
+    int steps_since_deal;
+    int obs_len;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return SKYJO_E_CUDA + (int)e;
+}
+#define CU(call)                                      \
+    do {                                              \
+        cudaError_t _e = (call);                      \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+    } while (0)
+
+static long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+static bool config_ok(const SkyjoConfig *c) {
+    return c && c->num_players >= 1 && c->num_players <= SKYJO_MAX_PLAYERS &&  // skyjo.py:24-26
+           c->max_episode_steps >= 0 && c->max_episode_steps <= 0xFFFF;
+}
+
+struct Layout {
+    long long planes, next_planes, pile, episode, needs_deal, stats, stats_tmp, errflag, total;
+};
+static Layout layout_for(int N, long long B) {
+    const long long Bpad = align_up(B, TILE);
+    const long long np = num_planes(N);
+    Layout L;
+    long long off = 0;
+    L.planes = off;      off = align_up(off + np * Bpad * 16, 256);
+    L.next_planes = off; off = align_up(off + np * Bpad * 16, 256);
+    L.pile = off;        off = align_up(off + 2 * Bpad * PILE_ROW, 256);
+    L.episode = off;     off = align_up(off + Bpad * 4, 256);
+    L.needs_deal = off;  off = align_up(off + Bpad, 256);
+    L.stats = off;       off = align_up(off + (long long)STAT_SLOTS * NUM_STATS * 8, 256);
+    L.stats_tmp = off;   off = align_up(off + NUM_STATS * 8, 256);
+    L.errflag = off;     off = align_up(off + 4, 256);
+    L.total = off;
+    return L;
+}
+
+extern "C" {
+
+int skyjo_abi_version(void) { return SKYJO_ABI_VERSION; }
+const char *skyjo_last_error(void) { return g_err; }
+
+int skyjo_obs_len(const SkyjoConfig *cfg) {
+    if (!config_ok(cfg)) return -1;
+    return cfg->observe_other_player_indirect ? 31 : 19 + 12 * cfg->num_players;  // skyjo.py:43-45
+}
+
+int64_t skyjo_state_bytes(const SkyjoConfig *cfg, int64_t num_envs) {
+    if (!config_ok(cfg) || num_envs <= 0) return -1;
+    return layout_for(cfg->num_players, num_envs).total;
+}
+
+int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t seed, int64_t first_global_env_id,
+                 void *state_dev, int64_t state_bytes, SkyjoHandle **out) {
+    if (!out) return fail(SKYJO_E_INVALID, "null out pointer");
+    *out = nullptr;
+    if (!config_ok(cfg)) return fail(SKYJO_E_INVALID, "invalid config: num_players must be 1..12");
+    if (num_envs <= 0 || first_global_env_id < 0) return fail(SKYJO_E_INVALID, "num_envs must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SKYJO_E_NO_DEVICE, "no CUDA device: libskyjo_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(SKYJO_E_INVALID, "bad device index");
+    const Layout L = layout_for(cfg->num_players, num_envs);
+    if (!state_dev || state_bytes < L.total || ((uintptr_t)state_dev & 255)) {
+        return fail(SKYJO_E_INVALID, "state buffer null, too small or not 256-byte aligned");
+    }
+    CU(cudaSetDevice(device));
+    SkyjoHandle *h = new (std::nothrow) SkyjoHandle();
+    if (!h) return fail(SKYJO_E_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->device = device;
+    h->B = num_envs;
+    h->Bpad = align_up(num_envs, TILE);
+    h->seed = seed;
+    h->first_env = (unsigned long long)first_global_env_id;
+    uint8_t *base = (uint8_t *)state_dev;
+    h->st.planes = (uint4 *)(base + L.planes);
+    h->st.next_planes = (uint4 *)(base + L.next_planes);
+    h->st.pile = base + L.pile;
+    h->st.episode = (uint32_t *)(base + L.episode);
+    h->st.needs_deal = base + L.needs_deal;
+    h->st.stats = (unsigned long long *)(base + L.stats);
+    h->stats_tmp = (long long *)(base + L.stats_tmp);
+    h->st.errflag = (uint32_t *)(base + L.errflag);
+    h->bound = false;
+    h->bulk_ok = 0;
+    h->t = 0;
+    h->launches = 0;
+    h->steps_since_deal = 0;
+    h->obs_len = skyjo_obs_len(cfg);
+    cudaError_t e = cudaMemset(state_dev, 0, (size_t)L.total);
+    if (e != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaMemset(state)");
+    }
+    *out = h;
+    return SKYJO_OK;
+}
+
+int skyjo_destroy(SkyjoHandle *h) {
+    delete h;
+    return SKYJO_OK;
+}
+
+int skyjo_bind_outputs(SkyjoHandle *h, const SkyjoOutputs *o) {
+    if (!h || !o) return fail(SKYJO_E_INVALID, "null argument");
+    if (!o->obs_dev || !o->action_mask_dev || !o->agent_dev || !o->done_dev || !o->reward_dev || !o->final_score_dev)
+        return fail(SKYJO_E_INVALID, "all six output buffers are required");
+    if (((uintptr_t)o->reward_dev & 7) || ((uintptr_t)o->final_score_dev & 7))
+        return fail(SKYJO_E_INVALID, "reward / final_score must be 8-byte aligned");
+    h->outs = *o;
+    h->bulk_ok = (((uintptr_t)o->obs_dev & 15) == 0 && ((uintptr_t)o->action_mask_dev & 15) == 0) ? 1 : 0;
+    h->bound = true;
+    return SKYJO_OK;
+}
+
+static StepParams make_params(const SkyjoHandle *h) {
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.st = h->st;
+    p.obs = (int8_t *)h->outs.obs_dev;
+    p.mask = (int8_t *)h->outs.action_mask_dev;
+    p.agent = (int8_t *)h->outs.agent_dev;
+    p.done = (uint8_t *)h->outs.done_dev;
+    p.reward = (double *)h->outs.reward_dev;
+    p.final_score = (double *)h->outs.final_score_dev;
+    p.B = h->B;
+    p.Bpad = h->Bpad;
+    p.first_env = h->first_env;
+    p.seed = h->seed;
+    p.t = h->t;
+    p.score_penalty = h->cfg.score_penalty;
+    p.mean_reward = h->cfg.mean_reward;
+    p.reward_refunded = h->cfg.reward_refunded;
+    p.auto_reset = h->cfg.auto_reset;
+    p.max_steps = h->cfg.max_episode_steps;
+    p.bulk_ok = h->bulk_ok;
+    return p;
+}
+
+static int launch_deal(SkyjoHandle *h, int flagged, int target_next, const int8_t *decks, const uint8_t *flips,
+                       cudaStream_t s) {
+    DealParams d;
+    d.st = h->st;
+    d.B = h->B;
+    d.Bpad = h->Bpad;
+    d.first_env = h->first_env;
+    d.seed = h->seed;
+    d.N = h->cfg.num_players;
+    d.indirect = h->cfg.observe_other_player_indirect ? 1 : 0;
+    d.flagged = flagged;
+    d.target_next = target_next;
+    d.decks = decks;
+    d.flips = flips;
+    const long long per = flagged ? DEAL_SCAN : DEAL_THREADS;
+    const unsigned grid = (unsigned)((h->B + per - 1) / per);
+    deal_kernel<<<grid, DEAL_THREADS, 0, s>>>(d);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return SKYJO_OK;
+}
+
+static int reset_common(SkyjoHandle *h, const int8_t *decks, const uint8_t *flips, cudaStream_t s) {
+    if (!h) return fail(SKYJO_E_INVALID, "null handle");
+    if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemsetAsync(h->st.needs_deal, 0, (size_t)h->Bpad, s));
+    int rc = launch_deal(h, 0, 0, decks, flips, s);
+    if (rc) return rc;
+    if (h->cfg.auto_reset) {
+        rc = launch_deal(h, 0, 1, nullptr, nullptr, s);
+        if (rc) return rc;
+    }
+    h->steps_since_deal = 0;
+    StepParams p = make_params(h);
+    CU(kObserve[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, -1, p.obs, p.mask, 1,
+                                        h->bulk_ok, s));
+    h->launches += 1;
+    return SKYJO_OK;
+}
+
+int skyjo_reset(SkyjoHandle *h, void *stream) { return reset_common(h, nullptr, nullptr, (cudaStream_t)stream); }
+
+int skyjo_reset_injected(SkyjoHandle *h, const int8_t *decks_dev, const uint8_t *flips_dev, void *stream) {
+    if (!decks_dev || !flips_dev) return fail(SKYJO_E_INVALID, "decks and flips are required");
+    return reset_common(h, decks_dev, flips_dev, (cudaStream_t)stream);
+}
+
+int skyjo_seed(SkyjoHandle *h, uint64_t seed, void *stream) {
+    if (!h) return fail(SKYJO_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    h->seed = seed;
+    h->t = 0;
+    CU(cudaMemsetAsync(h->st.episode, 0, (size_t)h->Bpad * 4, (cudaStream_t)stream));
+    return skyjo_reset(h, stream);
+}
+
+// Refill cadence of the pre-dealt "next" episodes.  With the in-kernel legal policy no env can
+// finish twice within 8 steps (an episode lasts >= 21 act() calls), so one flagged deal launch
+// per 8 steps suffices; external actions may be illegal and end an episode at once, so deal
+// after every step.
+static int deal_period(const SkyjoHandle *h, bool policy) {
+    if (!policy) return 1;
+    if (h->cfg.max_episode_steps > 0 && h->cfg.max_episode_steps < 16) return 1;
+    return 8;
+}
+
+static int step_once(SkyjoHandle *h, const void *actions, int dtype, bool policy, cudaStream_t s) {
+    StepParams p = make_params(h);
+    p.actions = actions;
+    p.action_dtype = dtype;
+    CU(kStep[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, policy, s));
+    h->launches += 1;
+    h->t += 1;
+    if (h->cfg.auto_reset && ++h->steps_since_deal >= deal_period(h, policy)) {
+        h->steps_since_deal = 0;
+        return launch_deal(h, 1, 1, nullptr, nullptr, s);
+    }
+    return SKYJO_OK;
+}
+
+int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *stream) {
+    if (!h || !actions_dev) return fail(SKYJO_E_INVALID, "null argument");
+    if (action_dtype < SKYJO_ACT_U8 || action_dtype > SKYJO_ACT_I64) return fail(SKYJO_E_INVALID, "bad action dtype");
+    if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
+    CU(cudaSetDevice(h->device));
+    return step_once(h, actions_dev, action_dtype, false, (cudaStream_t)stream);
+}
+
+int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream) {
+    if (!h || n_steps < 0) return fail(SKYJO_E_INVALID, "bad argument");
+    if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
+    CU(cudaSetDevice(h->device));
+    // a pending external-action cadence must not be stretched: flush it first
+    if (h->cfg.auto_reset && h->steps_since_deal > 0) {
+        h->steps_since_deal = 0;
+        int rc = launch_deal(h, 1, 1, nullptr, nullptr, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n_steps; ++i) {
+        int rc = step_once(h, nullptr, 0, true, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    if (h->cfg.auto_reset && h->steps_since_deal > 0) {
+        h->steps_since_deal = 0;
+        return launch_deal(h, 1, 1, nullptr, nullptr, (cudaStream_t)stream);
+    }
+    return SKYJO_OK;
+}
+
+int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host, int8_t *mask_host,
+                    int8_t *agent_host, uint8_t *done_host, double *reward_host, void *stream) {
+    if (!h || !actions_host) return fail(SKYJO_E_INVALID, "null argument");
+    if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    // the agent buffer doubles as the staging area of the uint8 actions: it is rewritten by the step
+    uint8_t *act_dev = (uint8_t *)h->outs.agent_dev;
+    CU(cudaMemcpyAsync(act_dev, actions_host, (size_t)h->B, cudaMemcpyHostToDevice, s));
+    int rc = step_once(h, act_dev, SKYJO_ACT_U8, false, s);
+    if (rc) return rc;
+    const size_t B = (size_t)h->B, N = (size_t)h->cfg.num_players;
+    if (obs_host) CU(cudaMemcpyAsync(obs_host, h->outs.obs_dev, B * (size_t)h->obs_len, cudaMemcpyDeviceToHost, s));
+    if (mask_host) CU(cudaMemcpyAsync(mask_host, h->outs.action_mask_dev, B * 26, cudaMemcpyDeviceToHost, s));
+    if (agent_host) CU(cudaMemcpyAsync(agent_host, h->outs.agent_dev, B, cudaMemcpyDeviceToHost, s));
+    if (done_host) CU(cudaMemcpyAsync(done_host, h->outs.done_dev, B, cudaMemcpyDeviceToHost, s));
+    if (reward_host) CU(cudaMemcpyAsync(reward_host, h->outs.reward_dev, B * N * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return SKYJO_OK;
+}
+
+int skyjo_observe(SkyjoHandle *h, int agent, void *obs_dev, void *mask_dev, void *stream) {
+    if (!h || !obs_dev || !mask_dev) return fail(SKYJO_E_INVALID, "null argument");
+    if (agent >= h->cfg.num_players) return fail(SKYJO_E_INVALID, "agent out of range");
+    CU(cudaSetDevice(h->device));
+    StepParams p = make_params(h);
+    const int bulk = (((uintptr_t)obs_dev & 15) == 0 && ((uintptr_t)mask_dev & 15) == 0) ? 1 : 0;
+    CU(kObserve[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, agent, (int8_t *)obs_dev,
+                                        (int8_t *)mask_dev, 0, bulk, (cudaStream_t)stream));
+    h->launches += 1;
+    return SKYJO_OK;
+}
+
+int skyjo_stats_device(SkyjoHandle *h, int64_t *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(SKYJO_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    stats_reduce_kernel<<<1, NUM_STATS, 0, (cudaStream_t)stream>>>(h->st.stats, (long long *)out_dev);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return SKYJO_OK;
+}
+
+int skyjo_stats_host(SkyjoHandle *h, int64_t *out_host, void *stream) {
+    if (!h || !out_host) return fail(SKYJO_E_INVALID, "null argument");
+    int rc = skyjo_stats_device(h, (int64_t *)h->stats_tmp, stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_host, h->stats_tmp, NUM_STATS * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return SKYJO_OK;
+}
+
+int skyjo_stats_clear(SkyjoHandle *h, void *stream) {
+    if (!h) return fail(SKYJO_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemsetAsync(h->st.stats, 0, (size_t)STAT_SLOTS * NUM_STATS * 8, (cudaStream_t)stream));
+    return SKYJO_OK;
+}
+
+int skyjo_export_debug(SkyjoHandle *h, int64_t env0, int64_t count, SkyjoEnvDebug *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(SKYJO_E_INVALID, "null argument");
+    if (env0 < 0 || count <= 0 || env0 + count > h->B) return fail(SKYJO_E_INVALID, "env range out of bounds");
+    CU(cudaSetDevice(h->device));
+    const unsigned grid = (unsigned)((count + 127) / 128);
+    export_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->st, h->Bpad, h->cfg.num_players,
+                                                          h->cfg.observe_other_player_indirect ? 1 : 0, env0, count,
+                                                          out_dev);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return SKYJO_OK;
+}
+
+int skyjo_check(SkyjoHandle *h, void *stream) {
+    if (!h) return fail(SKYJO_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    uint32_t flag = 0;
+    CU(cudaMemcpyAsync(&flag, h->st.errflag, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag) {
+        snprintf(g_err, sizeof(g_err), "device consistency flag 0x%x:%s%s%s", flag,
+                 (flag & ERR_NEXT_NOT_READY) ? " next episode was not dealt in time" : "",
+                 (flag & ERR_BAD_DECK) ? " injected deck outside -2..12 or >15 copies of a value" : "",
+                 (flag & ERR_BAD_FLIPS) ? " injected flips invalid" : "");
+        return SKYJO_E_STATE;
+    }
+    return SKYJO_OK;
+}
+
+int64_t skyjo_step_count(const SkyjoHandle *h) { return h ? (int64_t)h->t : -1; }
+int skyjo_set_step_count(SkyjoHandle *h, int64_t t) {
+    if (!h || t < 0) return fail(SKYJO_E_INVALID, "bad argument");
+    h->t = (unsigned long long)t;
+    h->steps_since_deal = h->cfg.auto_reset ? 1 : 0;  // force a refill after the next step
+    return SKYJO_OK;
+}
+int64_t skyjo_launch_count(const SkyjoHandle *h) { return h ? h->launches : -1; }
+
+// ---- host twins of the device RNG (same header, host compilation path) ---------------------
+void skyjo_host_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    U4 c = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    U4 r = philox4x32_10(c, key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+void skyjo_host_deck(uint64_t seed, uint64_t genv, uint32_t episode, int8_t out[SKYJO_DECK]) {
+    for (int i = 0; i < SKYJO_DECK; ++i) out[i] = (int8_t)(i / 10 - 2);
+    U4 blk = {0, 0, 0, 0};
+    for (int i = SKYJO_DECK - 1; i >= 1; --i) {
+        const int k = SKYJO_DECK - 1 - i;
+        if ((k & 3) == 0) blk = rng_block(seed, genv, PURPOSE_DEAL, episode, (uint32_t)(k >> 2));
+        const uint32_t r = (k & 3) == 0 ? blk.x : (k & 3) == 1 ? blk.y : (k & 3) == 2 ? blk.z : blk.w;
+        const int j = (int)bounded(r, (uint32_t)(i + 1));
+        const int8_t t = out[i];
+        out[i] = out[j];
+        out[j] = t;
+    }
+}
+
+void skyjo_host_flips(uint64_t seed, uint64_t genv, uint32_t episode, int num_players, uint8_t *out) {
+    for (int q = 0; q < num_players; ++q) {
+        U4 r = rng_block(seed, genv, PURPOSE_FLIPS, episode, (uint32_t)q);
+        uint32_t a = bounded(r.x, 12u), b = bounded(r.y, 11u);
+        if (b >= a) b += 1u;
+        out[2 * q] = (uint8_t)a;
+        out[2 * q + 1] = (uint8_t)b;
+    }
+}
+
+int skyjo_host_policy(uint64_t seed, uint64_t genv, uint64_t t, uint32_t legal_bits) {
+    if (legal_bits == 0) return -1;
+    return policy_pick(seed, genv, t, legal_bits);
+}
+
+}  // extern "C"

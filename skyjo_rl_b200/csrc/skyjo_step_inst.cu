@@ -1,0 +1,39 @@
+// skyjo_step_inst.cu -- instantiates the fused step / observe kernels for one player count.
+// Compiled once per N with -DSKYJO_N=<1..12> (build.py) so the 12 translation units build
+// in parallel.
+#include "skyjo_step.cuh"
+
+#ifndef SKYJO_N
+#error "compile with -DSKYJO_N=<num_players>"
+#endif
+
+#define SKYJO_CAT2(a, b) a##b
+#define SKYJO_CAT(a, b) SKYJO_CAT2(a, b)
+
+namespace skyjo {
+
+cudaError_t SKYJO_CAT(launch_step_, SKYJO_N)(const StepParams &p, bool indirect, bool policy, cudaStream_t s) {
+    constexpr int N = SKYJO_N;
+    const dim3 grid((unsigned)(p.Bpad / TILE)), block(TILE);
+    const size_t smem = (size_t)TILE * ((indirect ? 31 : 19 + 12 * N) + 26);
+    if (indirect) {
+        if (policy) step_kernel<N, true, true><<<grid, block, smem, s>>>(p);
+        else step_kernel<N, true, false><<<grid, block, smem, s>>>(p);
+    } else {
+        if (policy) step_kernel<N, false, true><<<grid, block, smem, s>>>(p);
+        else step_kernel<N, false, false><<<grid, block, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t SKYJO_CAT(launch_observe_, SKYJO_N)(const StepParams &p, bool indirect, int agent, int8_t *obs,
+                                                 int8_t *mask, int reset_outputs, int bulk_ok, cudaStream_t s) {
+    constexpr int N = SKYJO_N;
+    const dim3 grid((unsigned)(p.Bpad / TILE)), block(TILE);
+    const size_t smem = (size_t)TILE * ((indirect ? 31 : 19 + 12 * N) + 26);
+    if (indirect) observe_kernel<N, true><<<grid, block, smem, s>>>(p, agent, obs, mask, reset_outputs, bulk_ok);
+    else observe_kernel<N, false><<<grid, block, smem, s>>>(p, agent, obs, mask, reset_outputs, bulk_ok);
+    return cudaGetLastError();
+}
+
+}  // namespace skyjo

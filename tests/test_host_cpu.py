@@ -1,0 +1,87 @@
+"""Host-side checks that need no GPU: the C-ABI library loads, exports every symbol the header
+declares, validates configs, fails loudly without a device, and its host RNG twins agree with
+the oracle's independent restatement."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from skyjo_rl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    header = open(os.path.join(ROOT, "include", "skyjo_b200.h")).read()
+    declared = set(re.findall(r"\b(skyjo_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.skyjo_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    assert C.sizeof(_lib.SkyjoConfig) == 40
+    assert C.sizeof(_lib.SkyjoOutputs) == 48
+    assert C.sizeof(_lib.SkyjoEnvDebug) == 536
+
+
+def test_obs_len_and_state_bytes():
+    L = _lib.load()
+    for N in range(1, 13):
+        cfg = _lib.SkyjoConfig(N, 0, 2.0, 1.0, 0.0, 1, 0)
+        assert L.skyjo_obs_len(C.byref(cfg)) == 19 + 12 * N          # reference skyjo.py:43-45
+        cfg.observe_other_player_indirect = 1
+        assert L.skyjo_obs_len(C.byref(cfg)) == 31
+        nbytes = L.skyjo_state_bytes(C.byref(cfg), 1000)
+        assert nbytes > 0 and nbytes % 256 == 0
+    for bad in (0, 13, -1):
+        cfg = _lib.SkyjoConfig(bad, 0, 2.0, 1.0, 0.0, 1, 0)
+        assert L.skyjo_obs_len(C.byref(cfg)) == -1                  # skyjo.py:24-26
+        assert L.skyjo_state_bytes(C.byref(cfg), 10) == -1
+
+
+def test_create_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    L = _lib.load()
+    cfg = _lib.SkyjoConfig(4, 0, 2.0, 1.0, 0.0, 1, 0)
+    h = C.c_void_p()
+    rc = L.skyjo_create(C.byref(cfg), 0, 128, 0, 0, None, 0, C.byref(h))
+    assert rc == 4 and b"no CPU fallback" in L.skyjo_last_error()
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    with pytest.raises(RuntimeError):
+        BatchedSkyjoEnv(num_envs=8, num_players=2)
+
+
+def test_host_rng_twins_match_oracle_restatement():
+    L = _lib.load()
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        seed, env, ep = int(rng.integers(2**62)), int(rng.integers(2**40)), int(rng.integers(2**31))
+        d = (C.c_int8 * 150)()
+        L.skyjo_host_deck(seed, env, ep, d)
+        assert list(d) == O.rng_deck(seed, env, ep).tolist()
+        f = (C.c_uint8 * 24)()
+        L.skyjo_host_flips(seed, env, ep, 12, f)
+        assert list(f) == O.rng_flips(seed, env, ep, 12).reshape(-1).tolist()
+        mask = (rng.random(26) < 0.5).astype(np.int8)
+        mask[int(rng.integers(26))] = 1
+        bits = int(sum(1 << i for i in range(26) if mask[i]))
+        t = int(rng.integers(2**40))
+        assert L.skyjo_host_policy(seed, env, t, bits) == O.rng_policy(seed, env, t, mask)
+    out = (C.c_uint32 * 4)()
+    L.skyjo_host_philox4x32_10((C.c_uint32 * 4)(0, 0, 0, 0), (C.c_uint32 * 2)(0, 0), out)
+    assert list(out) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+def test_spaces_match_reference_bounds():
+    from skyjo_rl_b200.spaces import Box, Discrete
+    b = Box(low=-24, high=127, shape=(67,), dtype=np.int8)   # reference skyjo_env.py:129-134
+    assert b.shape == (67,) and b.low.min() == -24 and b.high.max() == 127
+    assert Discrete(26).n == 26                               # skyjo_env.py:146-151
