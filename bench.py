@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- SkyJo env-steps/sec of the fused step + mask + observe kernel on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # N=1: this process
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one launch of the fused kernel = one env-step (SkyjoGame.act + the next agent's
+observation and action mask, i.e. one iteration of reference rlskyjo/game/sample_game.py:10-21)
+for EVERY env of the batch, with the uniform legal policy drawn in-kernel and auto-reset on.
+Workload = BASELINE.json configs[1]: 4-player SkyJo, 2^20 lockstep envs per GPU, direct
+observations (D = 67).  Envs shard over GPUs by global env id (weak scaling: 2^20 per GPU);
+the only collective is the all-reduce of the 32-entry statistics vector every 64 steps.
+
+Printed JSON (rank 0): value = whole-job env-steps/s with state resident in HBM; e2e = the same
+metric through the host-buffer C-ABI entry (skyjo_step_host: pinned actions in, obs / mask /
+agent / done / reward out, copies inside the timed region); roofline = algorithmic bytes of one
+launch (36N + 119 B per env-step with the policy fused) / the step kernel's mean
+device time, against the measured HBM copy bandwidth; cpu_baseline = the C oracle port of the
+reference's loop on this box's host cores.
+
+`--impl reference` times that CPU implementation alone (all host threads) on the same
+workload definition.  The reference is pure Python (no C sources to compile into oracle/_ref),
+so the arm runs the oracle port; see DESIGN.md.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SkyJo env-steps/sec"
+UNIT = "env-steps/s"
+L2_MB = 126.0
+
+
+def algorithmic_bytes_per_step(N, indirect, action_bytes=0):
+    # read 24N+24, write 48, outputs D+28, + action bytes
+    return (24 * N + 131 + action_bytes) if indirect else (36 * N + 119 + action_bytes)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic(key):
+    """Per-launch DRAM bytes of the step kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(key)
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+# ---- CPU baseline (oracle port) -------------------------------------------------------------
+_POOL = None
+
+
+def cpu_rollout(N, indirect, games_per_thread, threads, seed=0, env0=0):
+    """All threads play `games_per_thread` full games each; returns (env-steps, seconds)."""
+    global _POOL
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+    O.lib()
+    if _POOL is None or _POOL._max_workers != threads:
+        _POOL = ThreadPoolExecutor(max_workers=threads)  # ctypes releases the GIL
+
+    def work(i):
+        return O.rollout(N, 2.0, indirect, seed, env0 + i * games_per_thread, games_per_thread)[0]
+
+    t0 = time.perf_counter()
+    steps = sum(_POOL.map(work, range(threads)))
+    return steps, time.perf_counter() - t0
+
+
+def python_reference_rate(N, seconds=4.0):
+    """Optional: the unmodified Python reference (baseline/_ref copy) on one core, if importable."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "rlskyjo")):
+        return None
+    try:
+        sys.path.insert(0, ref)
+        import numpy as np
+        from rlskyjo.game.skyjo import SkyjoGame
+        from rlskyjo.models.random_admissible_policy import policy_ra
+        g = SkyjoGame(num_players=N)
+        steps = 0
+        rng = np.random.default_rng(0)
+        for warm in (True, False):
+            t0 = time.perf_counter()
+            steps = 0
+            while time.perf_counter() - t0 < (1.0 if warm else seconds):
+                g.reset()
+                while not g.is_terminated:
+                    pid, _ = g.expected_action
+                    obs, mask = g.collect_observation(pid)
+                    g.act(pid, policy_ra(obs, mask, rng))
+                    steps += 1
+            dt = time.perf_counter() - t0
+        return steps / dt
+    except Exception:  # noqa: BLE001
+        return None
+    finally:
+        if ref in sys.path:
+            sys.path.remove(ref)
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.sm_max = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---- arms ----------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    N, ind = args.players, args.indirect
+    threads = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    # bounded sample per step so that the whole run stays near args.cpu_budget seconds
+    ep_len = {1: 46, 2: 76, 3: 106, 4: 133, 8: 240, 12: 341}.get(N, 30 * N)
+    games = int(args.cpu_budget * 1.0e6 / ep_len / max(total, 1))
+    games = max(2, min(games, 20000))
+    for w in range(args.warmup):
+        cpu_rollout(N, ind, games, threads, env0=w * threads * games)
+    steps = 0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        s, _ = cpu_rollout(N, ind, games, threads, env0=(args.warmup + k) * threads * games)
+        steps += s
+    dt = time.perf_counter() - t0
+    value = steps / dt
+    sample = f"{games} full games per thread per step x {threads} threads, C oracle port, Philox deal + uniform legal policy"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    N = args.players
+    D = 31 if args.indirect else 19 + 12 * N
+    per_step_mb = args.envs * (16 * (1 + (N + 1) // 2) * 2 + D + 28 + 8) / 1e6
+    return {
+        "workload": f"{N}-player SkyJo, {args.envs} lockstep envs per GPU, uniform legal policy in-kernel, "
+                    f"fused step+mask+observe, {'indirect' if args.indirect else 'direct'} obs D={D}, auto-reset",
+        "num_players": N, "envs_per_gpu": args.envs, "global_envs": args.envs * world, "obs_len": D,
+        "parallelism": f"env-sharded x{world}, stats all-reduce every 64 steps",
+        "l2": f"no flush: ~{per_step_mb:.0f} MB touched per step vs {L2_MB:.0f} MB L2 (inputs larger than L2)",
+        "preroll_steps": args.preroll,
+    }
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, B, K, W = args.players, args.envs, args.steps, args.warmup
+    env = BatchedSkyjoEnv(num_envs=B, num_players=N, observe_other_player_indirect=args.indirect,
+                          device=dev, seed=args.seed, first_global_env_id=rank * B)
+    env.reset()
+    stats_vec = None
+
+    def run_steps(n):
+        nonlocal stats_vec
+        done = 0
+        while done < n:
+            c = min(64, n - done)
+            env.step_random(c)
+            done += c
+            if world > 1:
+                stats_vec = env.stats_tensor()
+                dist.all_reduce(stats_vec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    run_steps(args.preroll)          # desynchronise the episodes: steady-state mix of phases
+    run_steps(W)
+    env.clear_stats()
+    l0 = env.launch_count
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record()
+    run_steps(K)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = env.launch_count - l0
+    value = B * world * K / (ms * 1e-3)
+
+    # roofline of the dominant kernel: mean device time of the step kernel from per-launch events
+    prof = env.step_random_profile(min(K, 512))
+    step_us = 1e3 * prof["step_ms"] / max(prof["step_launches"], 1)
+    alg = algorithmic_bytes_per_step(N, args.indirect) * B
+    peak, peak_src = hbm_peak()
+    achieved = alg / (step_us * 1e-6) / 1e9
+    key = f"step_N{N}_{'indirect' if args.indirect else 'direct'}_B{B}"
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": committed_traffic(key), "kernel": "skyjo::step_kernel", "kernel_us": step_us,
+                "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                "deal_kernel_share": prof["deal_ms"] / max(prof["deal_ms"] + prof["step_ms"], 1e-9)}
+    stats = env.stats(all_reduce=world > 1)
+    env.check()
+
+    # end to end through the host-buffer C-ABI entry
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e = run_e2e(args, env, dev, rank, world)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            ep_len = {1: 46, 2: 76, 3: 106, 4: 133, 8: 240, 12: 341}.get(N, 30 * N)
+            games = max(2, int(args.cpu_budget * 1.0e6 / ep_len / threads))
+            cpu_rollout(N, args.indirect, max(2, games // 10), threads)
+            s, dt = cpu_rollout(N, args.indirect, games, threads)
+            cpu = {"value": s / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{games} full games per thread x {threads} threads ({s} env-steps), C oracle port of "
+                             "sample_game.py:10-21 with the same Philox deal and uniform legal policy"}
+            pr = python_reference_rate(N) if args.python_reference else None
+            if pr:
+                cpu["python_reference_1core"] = pr
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, env, dev, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+
+    N, B, T = args.players, args.envs, args.e2e_steps
+    D = env.obs_len
+    kw = dict(num_envs=B, num_players=N, observe_other_player_indirect=args.indirect, device=dev,
+              seed=args.seed + 1, first_global_env_id=rank * B)
+    Tw = 3
+    # record a legal action sequence on the device (untimed), then replay it from pinned host memory
+    rec = BatchedSkyjoEnv(**kw)
+    rec.reset()
+    acts = torch.empty((T + Tw, B), dtype=torch.uint8).pin_memory()
+    for t in range(T + Tw):
+        a = torch.multinomial(rec.action_mask.float(), 1).squeeze(1).to(torch.uint8)
+        rec.step(a)
+        acts[t].copy_(a)
+    torch.cuda.synchronize(dev)
+    rec.close()
+    del rec
+    e = BatchedSkyjoEnv(**kw)
+    e.reset()
+    obs_h = torch.empty((B, D), dtype=torch.int8).pin_memory()
+    mask_h = torch.empty((B, 26), dtype=torch.int8).pin_memory()
+    agent_h = torch.empty(B, dtype=torch.int8).pin_memory()
+    done_h = torch.empty(B, dtype=torch.uint8).pin_memory()
+    rew_h = torch.empty((B, N), dtype=torch.float64).pin_memory()
+    for t in range(Tw):
+        e.step_host(acts[t], obs_h, mask_h, agent_h, done_h, rew_h)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for t in range(Tw, Tw + T):
+        e.step_host(acts[t], obs_h, mask_h, agent_h, done_h, rew_h)   # synchronises every step
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    illegal = e.stats()["illegal"]
+    e.check()
+    assert illegal == 0, "replayed actions must be legal"
+    return {"value": B * world * T / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": B,
+            "d2h_bytes_per_step": B * (D + 26 + 1 + 1 + 8 * N), "steps": T,
+            "api": "skyjo_step_host (C ABI) via BatchedSkyjoEnv.step_host, pinned host buffers"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--players", type=int, default=4)
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--indirect", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--preroll", type=int, default=640)
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="CPU-seconds of oracle work (baseline sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--python-reference", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -161,6 +161,11 @@ int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *
 /* n_steps fused launches with the uniform legal policy (random_admissible_policy.py:26-28)
  * drawn in-kernel: the loop of sample_game.py:10-21. */
 int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream);
+/* skyjo_step_random with every kernel bracketed by CUDA events on `stream`: returns the summed
+ * device time (ms) and launch counts of the step kernels and of the deal kernels; synchronises.
+ * Measurement aid for bench.py's roofline figure. */
+int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double *step_ms,
+                              double *deal_ms, int64_t *n_step_launches, int64_t *n_deal_launches);
 /* Host-buffer entry for end-to-end use: copies actions (uint8[B]) to the device, steps,
  * copies obs / mask / agent / done / reward back; synchronises.  Null outputs are skipped. */
 int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host,

@@ -27,7 +27,7 @@ STAT_NAMES = [
 EXPORTS = [
     "skyjo_abi_version", "skyjo_last_error", "skyjo_obs_len", "skyjo_state_bytes", "skyjo_create",
     "skyjo_destroy", "skyjo_bind_outputs", "skyjo_reset", "skyjo_reset_injected", "skyjo_seed",
-    "skyjo_step", "skyjo_step_random", "skyjo_step_host", "skyjo_observe", "skyjo_stats_device",
+    "skyjo_step", "skyjo_step_random", "skyjo_step_random_profile", "skyjo_step_host", "skyjo_observe", "skyjo_stats_device",
     "skyjo_stats_host", "skyjo_stats_clear", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
     "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
     "skyjo_host_policy",
@@ -110,6 +110,8 @@ def load():
         "skyjo_seed": (i32, [vp, u64, vp]),
         "skyjo_step": (i32, [vp, vp, i32, vp]),
         "skyjo_step_random": (i32, [vp, i32, vp]),
+        "skyjo_step_random_profile": (i32, [vp, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                             C.POINTER(i64), C.POINTER(i64)]),
         "skyjo_step_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "skyjo_observe": (i32, [vp, i32, vp, vp, vp]),
         "skyjo_stats_device": (i32, [vp, vp, vp]),

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "../../include/skyjo_b200.h"
 #include "skyjo_deal.cuh"
@@ -46,7 +47,26 @@ struct SkyjoHandle {
     long long launches;
     int steps_since_deal;
     int obs_len;
+    // optional per-kernel event timing (skyjo_step_random_profile)
+    bool profiling;
+    std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
+    std::vector<int> prof_kind;            // 0 step kernel, 1 deal kernel
 };
+
+static void prof_begin(SkyjoHandle *h, int kind, cudaStream_t s) {
+    if (!h->profiling) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    h->prof_events.push_back(a);
+    h->prof_events.push_back(b);
+    h->prof_kind.push_back(kind);
+    cudaEventRecord(a, s);
+}
+static void prof_end(SkyjoHandle *h, cudaStream_t s) {
+    if (!h->profiling) return;
+    cudaEventRecord(h->prof_events.back(), s);
+}
 
 static thread_local char g_err[512] = "";
 
@@ -146,6 +166,7 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     h->launches = 0;
     h->steps_since_deal = 0;
     h->obs_len = skyjo_obs_len(cfg);
+    h->profiling = false;
     cudaError_t e = cudaMemset(state_dev, 0, (size_t)L.total);
     if (e != cudaSuccess) {
         delete h;
@@ -212,7 +233,9 @@ static int launch_deal(SkyjoHandle *h, int flagged, int target_next, const int8_
     d.flips = flips;
     const long long per = flagged ? DEAL_SCAN : DEAL_THREADS;
     const unsigned grid = (unsigned)((h->B + per - 1) / per);
+    prof_begin(h, 1, s);
     deal_kernel<<<grid, DEAL_THREADS, 0, s>>>(d);
+    prof_end(h, s);
     h->launches += 1;
     CU(cudaGetLastError());
     return SKYJO_OK;
@@ -267,7 +290,10 @@ static int step_once(SkyjoHandle *h, const void *actions, int dtype, bool policy
     StepParams p = make_params(h);
     p.actions = actions;
     p.action_dtype = dtype;
-    CU(kStep[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, policy, s));
+    prof_begin(h, 0, s);
+    cudaError_t le = kStep[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, policy, s);
+    prof_end(h, s);
+    CU(le);
     h->launches += 1;
     h->t += 1;
     if (h->cfg.auto_reset && ++h->steps_since_deal >= deal_period(h, policy)) {
@@ -303,6 +329,35 @@ int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream) {
         h->steps_since_deal = 0;
         return launch_deal(h, 1, 1, nullptr, nullptr, (cudaStream_t)stream);
     }
+    return SKYJO_OK;
+}
+
+int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double *step_ms, double *deal_ms,
+                              int64_t *n_step_launches, int64_t *n_deal_launches) {
+    if (!h || !step_ms || !deal_ms) return fail(SKYJO_E_INVALID, "null argument");
+    h->profiling = true;
+    int rc = skyjo_step_random(h, n_steps, stream);
+    h->profiling = false;
+    cudaError_t se = cudaStreamSynchronize((cudaStream_t)stream);
+    double sum[2] = {0.0, 0.0};
+    long long cnt[2] = {0, 0};
+    for (size_t i = 0; i < h->prof_kind.size(); ++i) {
+        float ms = 0.f;
+        if (se == cudaSuccess && cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]) == cudaSuccess) {
+            sum[h->prof_kind[i]] += ms;
+            cnt[h->prof_kind[i]] += 1;
+        }
+        cudaEventDestroy(h->prof_events[2 * i]);
+        cudaEventDestroy(h->prof_events[2 * i + 1]);
+    }
+    h->prof_events.clear();
+    h->prof_kind.clear();
+    if (rc) return rc;
+    CU(se);
+    *step_ms = sum[0];
+    *deal_ms = sum[1];
+    if (n_step_launches) *n_step_launches = cnt[0];
+    if (n_deal_launches) *n_deal_launches = cnt[1];
     return SKYJO_OK;
 }
 

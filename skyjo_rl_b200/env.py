@@ -184,6 +184,14 @@ class BatchedSkyjoEnv:
         assert self._has_reset, "reset() needs to be called before step"
         _lib.check(self._L.skyjo_step_random(self._h, int(n_steps), self._stream()))
 
+    def step_random_profile(self, n_steps):
+        """step_random with per-kernel CUDA-event timing; returns a dict of device times."""
+        sm, dm = C.c_double(0), C.c_double(0)
+        ns, nd = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.skyjo_step_random_profile(self._h, int(n_steps), self._stream(), C.byref(sm),
+                                                     C.byref(dm), C.byref(ns), C.byref(nd)))
+        return {"step_ms": sm.value, "deal_ms": dm.value, "step_launches": ns.value, "deal_launches": nd.value}
+
     def step_host(self, actions, obs=None, mask=None, agent=None, done=None, reward=None):
         """End-to-end host entry: numpy/pinned uint8 actions in, numpy outputs back
         (host-to-device and device-to-host copies included; synchronises)."""
