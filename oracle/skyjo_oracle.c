@@ -389,7 +389,7 @@ void sk_rng_reshuffle(void *vctx, int8_t *pile, int len) {
     sk_rng_shuffle_ctx *ctx = (sk_rng_shuffle_ctx *)vctx;
     int bins[15] = {0};
     for (int i = 0; i < len; ++i) bins[pile[i] + 2] += 1;
-    uint32_t q = ctx->q & 0xFFu;
+    uint32_t q = ctx->q & 0x7Fu; /* the product keeps 7 bits of the reshuffle index */
     for (int d = 0; d < len; ++d) {
         uint32_t remaining = (uint32_t)(len - d);
         uint32_t blk[4];

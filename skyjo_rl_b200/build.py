@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--fmad=false",
-]
+] + os.environ.get("SKYJO_NVCC_EXTRA", "").split()
 
 
 def _sources():

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -95,7 +96,7 @@ struct Layout {
     long long planes, next_planes, pile, episode, needs_deal, stats, stats_tmp, errflag, total;
 };
 static Layout layout_for(int N, long long B) {
-    const long long Bpad = align_up(B, TILE);
+    const long long Bpad = align_up(B, ENV_PAD);
     const long long np = num_planes(N);
     Layout L;
     long long off = 0;
@@ -143,18 +144,22 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
         return fail(SKYJO_E_INVALID, "state buffer null, too small or not 256-byte aligned");
     }
     CU(cudaSetDevice(device));
+    if (const char *g = getenv("SKYJO_L2_FETCH")) {  // experiment knob: L2 fetch granularity hint (32/64/128)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaGetLastError();
+    }
     SkyjoHandle *h = new (std::nothrow) SkyjoHandle();
     if (!h) return fail(SKYJO_E_INVALID, "out of host memory");
     h->cfg = *cfg;
     h->device = device;
     h->B = num_envs;
-    h->Bpad = align_up(num_envs, TILE);
+    h->Bpad = align_up(num_envs, ENV_PAD);
     h->seed = seed;
     h->first_env = (unsigned long long)first_global_env_id;
     uint8_t *base = (uint8_t *)state_dev;
-    h->st.planes = (uint4 *)(base + L.planes);
-    h->st.next_planes = (uint4 *)(base + L.next_planes);
-    h->st.pile = base + L.pile;
+    h->st.planes = (U128 *)(base + L.planes);
+    h->st.next_planes = (U128 *)(base + L.next_planes);
+    h->st.deck = base + L.pile;
     h->st.episode = (uint32_t *)(base + L.episode);
     h->st.needs_deal = base + L.needs_deal;
     h->st.stats = (unsigned long long *)(base + L.stats);

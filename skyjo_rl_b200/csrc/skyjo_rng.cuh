@@ -11,10 +11,12 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef SKYJO_HD
 #if defined(__CUDACC__)
 #define SKYJO_HD __host__ __device__ __forceinline__
 #else
 #define SKYJO_HD inline
+#endif
 #endif
 
 namespace skyjo {
@@ -71,14 +73,25 @@ SKYJO_HD uint32_t bounded(uint32_t r, uint32_t n) {
 #endif
 }
 
-// index (0-based, ascending) of the k-th set bit of m; k < popcount(m)
+// index (0-based, ascending) of the k-th set bit of m; k < popcount(m).  Branch-free binary
+// search over popcounts (a data-dependent loop would diverge across the warp).
 SKYJO_HD int nth_set_bit(uint32_t m, int k) {
-    for (int i = 0; i < k; ++i) m &= m - 1;
+    uint32_t pos = 0, kk = (uint32_t)k;
 #if defined(__CUDA_ARCH__)
-    return __ffs(m) - 1;
+#define SKYJO_POPC(x) ((uint32_t)__popc(x))
 #else
-    return __builtin_ctz(m);
+#define SKYJO_POPC(x) ((uint32_t)__builtin_popcount(x))
 #endif
+#pragma unroll
+    for (uint32_t w = 16; w >= 1; w >>= 1) {
+        const uint32_t c = SKYJO_POPC(m & ((1u << w) - 1u));
+        const bool up = kk >= c;
+        kk = up ? kk - c : kk;
+        pos = up ? pos + w : pos;
+        m = up ? m >> w : m;
+    }
+#undef SKYJO_POPC
+    return (int)pos;
 }
 
 // random_admissible_policy.py:26-28: uniform over the legal actions

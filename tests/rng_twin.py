@@ -68,7 +68,7 @@ def reshuffle(seed, env, episode, q, pile):
     out = [0] * n
     for d in range(n):
         remaining = n - d
-        blk = block(seed, env, PURPOSE_RESHUFFLE, episode, ((q & 0xFF) << 16) | remaining)
+        blk = block(seed, env, PURPOSE_RESHUFFLE, episode, ((q & 0x7F) << 16) | remaining)
         idx = bounded(blk[0], remaining)
         j = 0
         while idx >= bins[j]:

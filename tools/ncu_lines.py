@@ -34,14 +34,13 @@ def sass_page(report, kernel, launch):
     return blocks[min(launch, len(blocks) - 1)]
 
 
-def line_info(obj, kernel_mangled_sub):
+def line_info(obj, kernel_mangled_sub, prefer=None):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
     lines = []
     for f in sorted(os.listdir(tmp)):
         txt = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-        active, cur = False, ("?", 0)
-        inl = None
+        active, chain, fresh = False, [("?", 0)], True
         for ln in txt.splitlines():
             m = re.match(r"\s*\.text\.(\S+):", ln)
             if m:
@@ -53,11 +52,19 @@ def line_info(obj, kernel_mangled_sub):
                 continue
             m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', ln)
             if m:
-                cur = (os.path.basename(m.group(1)), int(m.group(2)))
-                inl = m.group(3)
+                if fresh:          # first annotation after an instruction starts a new chain
+                    chain, fresh = [], False
+                chain.append((os.path.basename(m.group(1)), int(m.group(2))))   # innermost first
                 continue
             m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*);", ln)
             if m:
+                fresh = True
+                cur = chain[0]
+                if prefer:
+                    for fr in chain:
+                        if fr[0] == prefer:
+                            cur = fr
+                            break
                 lines.append((int(m.group(1), 16), cur, m.group(2).strip()))
         if lines:
             break
@@ -71,6 +78,7 @@ def main():
     ap.add_argument("kernel", help="substring of the demangled name, e.g. 'step_kernel<4, 0, 1>'")
     ap.add_argument("--mangled", default=None, help="substring of the mangled name (default: derived)")
     ap.add_argument("--launch", type=int, default=0)
+    ap.add_argument("--file", default=None, help="attribute inlined code to its frame in this file (basename)")
     ap.add_argument("--top", type=int, default=40)
     a = ap.parse_args()
     blk = sass_page(a.report, a.kernel, a.launch)
@@ -80,7 +88,7 @@ def main():
     if mangled is None:
         m = re.search(r"(\w+)<(.*)>", a.kernel)
         mangled = m.group(1) if m else a.kernel
-    li = line_info(a.obj, mangled)
+    li = line_info(a.obj, mangled, a.file)
     rows = blk["rows"]
     print(f"# {blk['name']}: {len(rows)} SASS instructions in report, {len(li)} in object", file=sys.stderr)
     n = min(len(rows), len(li))
