@@ -199,8 +199,11 @@ SKYJO_HD void row_cards(const Row &r, uint32_t out[3]) {
 // with the mask applied to the card bytes; W0's meta bits and W3's spare byte are left as they are.
 SKYJO_HD uint32_t flags_to_bytemask(uint32_t f4) {  // 4 bits -> 4 bytes of 0x00 / 0xFF
 #if defined(__CUDA_ARCH__)
-    // bit i -> bit 8i+7, then replicate each byte's sign bit (PRMT sign mode)
-    return __byte_perm((f4 & 0xFu) * 0x10204080u, 0u, 0xBA98u);
+    // bit i -> bit 8i+7, then replicate each byte's sign bit (PRMT, selector msb = sign mode;
+    // __byte_perm ignores that bit, hence the PTX)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"((f4 & 0xFu) * 0x10204080u), "r"(0u), "r"(0xBA98u));
+    return d;
 #else
     return bitsFF(f4);
 #endif
