@@ -204,7 +204,8 @@ def run_reference(args, rank, world):
 def workload_config(args, world):
     N = args.players
     D = 31 if args.indirect else 19 + 12 * N
-    per_step_mb = args.envs * (16 * (1 + (N + 1) // 2) * 2 + D + 28 + 8) / 1e6
+    # per env-step: 1+N planes of 16 B read, plane 0 + (every other step) one row written, outputs
+    per_step_mb = args.envs * (16 * (1 + N) + 16 + 8 + D + 28) / 1e6
     return {
         "workload": f"{N}-player SkyJo, {args.envs} lockstep envs per GPU, uniform legal policy in-kernel, "
                     f"fused step+mask+observe, {'indirect' if args.indirect else 'direct'} obs D={D}, auto-reset",

@@ -1,0 +1,193 @@
+"""Single-game PettingZoo-style AEC view over one env of a batch.
+
+`SkyjoAECView` exposes the agent-environment-cycle surface the reference's consumers use
+(reference rlskyjo/environment/vanilla_env_example.py:14-35 and RLlib's PettingZooEnv):
+`reset / agent_iter / last / step(action | None) / observe / agent_selection / agents / rewards /
+_cumulative_rewards / dones / infos`, on top of any backend with the buffers of
+`BatchedSkyjoEnv` (created with `auto_reset=False`).
+
+The bookkeeping restates PettingZoo 1.14.0's `AECEnv` helpers as used by
+`SimpleSkyjoEnv.step` (reference rlskyjo/environment/skyjo_env.py:216-252): `_accumulate_rewards`,
+`_clear_rewards`, `_dones_step_first`, `_was_done_step`, and the wrapper stack of
+`skyjo_env.env()` (:19-26): `TerminateIllegalWrapper(illegal_reward=-1)` (done in-kernel: done
+code 2, offender -1, others 0), `AssertOutOfBoundsWrapper`, `OrderEnforcingWrapper`.
+PettingZoo itself is not installed here: this is a restatement from its documented behaviour
+and the notebook trace, functional rather than bit-pinned parity.
+"""
+import numpy as np
+
+from . import _lib
+
+
+def _np(x):
+    return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+
+
+class SkyjoAECView:
+    metadata = {"render.modes": ["human"], "name": "skyjo", "is_parallelizable": False,
+                "video.frames_per_second": 1}  # skyjo_env.py:31-36
+
+    def __init__(self, batched_env, index=0):
+        self.env = batched_env
+        self.index = int(index)
+        N = batched_env.num_players
+        self.possible_agents = [f"player_{i}" for i in range(N)]  # skyjo_env.py:116
+        self.agents = []
+        self.agent_selection = None
+        self._has_reset = False
+        self._skip_agent_selection = None
+
+    # ---- spaces (delegated) ---------------------------------------------------------------
+    def observation_space(self, agent):
+        return self.env.observation_space(agent)
+
+    def action_space(self, agent):
+        return self.env.action_space(agent)
+
+    @property
+    def num_agents(self):
+        return len(self.agents)
+
+    # ---- AEC API -----------------------------------------------------------------------------
+    def reset(self):
+        """skyjo_env.py:254-267"""
+        self.env.reset()
+        self.agents = self.possible_agents[:]
+        self.rewards = {a: 0 for a in self.agents}
+        self._cumulative_rewards = {a: 0 for a in self.agents}
+        self.dones = {a: False for a in self.agents}
+        self.infos = {a: {} for a in self.agents}
+        self.agent_selection = self._expected_agent()
+        self._skip_agent_selection = None
+        self._has_reset = True
+
+    def seed(self, seed=None):
+        if seed is not None:
+            self.env.seed(seed)
+            self.reset_after_seed()
+
+    def reset_after_seed(self):
+        self.agents = self.possible_agents[:]
+        self.rewards = {a: 0 for a in self.agents}
+        self._cumulative_rewards = {a: 0 for a in self.agents}
+        self.dones = {a: False for a in self.agents}
+        self.infos = {a: {} for a in self.agents}
+        self.agent_selection = self._expected_agent()
+        self._skip_agent_selection = None
+        self._has_reset = True
+
+    def _expected_agent(self):
+        return f"player_{int(_np(self.env.agent_selection)[self.index])}"
+
+    def observe(self, agent):
+        """skyjo_env.py:199-214: observation dict of any named agent"""
+        assert self._has_reset, "reset() needs to be called before observe"  # OrderEnforcingWrapper
+        o = self.env.observe(int(agent.split("_")[-1]))
+        return {"observations": _np(o["observations"])[self.index].copy(),
+                "action_mask": _np(o["action_mask"])[self.index].copy()}
+
+    def last(self, observe=True):
+        agent = self.agent_selection
+        obs = self.observe(agent) if observe else None
+        return obs, self._cumulative_rewards[agent], self.dones[agent], self.infos[agent]
+
+    def agent_iter(self, max_iter=2 ** 63):
+        it = max_iter
+        while self.agents and it > 0:
+            it -= 1
+            yield self.agent_selection
+
+    def step(self, action):
+        """skyjo_env.py:216-252 under the wrapper stack of skyjo_env.env() (:19-26)"""
+        assert self._has_reset, "reset() needs to be called before step"
+        agent = self.agent_selection
+        if self.dones[agent]:
+            return self._was_done_step(action)
+        assert action is not None and 0 <= int(action) < _lib.NUM_ACTIONS, \
+            "action is not in action space"                     # AssertOutOfBoundsWrapper
+        # the batch steps in lockstep: every other env of the backend plays its first legal action
+        actions = np.argmax(_np(self.env.action_mask), axis=1).astype(np.uint8)
+        actions[self.index] = int(action)
+        self.env.step(actions)
+        code = int(_np(self.env.done_code)[self.index])
+        self.agent_selection = self._expected_agent()
+        if code != _lib.RUNNING:
+            rw = _np(self.env.rewards)[self.index]
+            if code == _lib.DONE_ILLEGAL:
+                self._cumulative_rewards[agent] = 0              # TerminateIllegalWrapper
+            self.rewards = {a: float(rw[int(a.split("_")[-1])]) for a in self.agents}
+            self.dones = {a: True for a in self.agents}
+        self._accumulate_rewards()
+        self._clear_rewards()
+        self._dones_step_first()
+
+    # ---- PettingZoo 1.14 AECEnv helpers ---------------------------------------------------
+    def _accumulate_rewards(self):
+        for a, r in self.rewards.items():
+            self._cumulative_rewards[a] += r
+
+    def _clear_rewards(self):
+        for a in self.rewards:
+            self.rewards[a] = 0
+
+    def _dones_step_first(self):
+        order = [a for a in self.agents if self.dones[a]]
+        if order:
+            self._skip_agent_selection = self.agent_selection
+            self.agent_selection = order[0]
+        return self.agent_selection
+
+    def _was_done_step(self, action):
+        if action is not None:
+            raise ValueError("when an agent is done, the only valid action is None")
+        agent = self.agent_selection
+        assert self.dones[agent], "an agent that was not done as attempted to be removed"
+        del self.dones[agent], self.rewards[agent], self._cumulative_rewards[agent], self.infos[agent]
+        self.agents.remove(agent)
+        order = [a for a in self.agents if self.dones[a]]
+        if order:
+            if self._skip_agent_selection is None:
+                self._skip_agent_selection = self.agent_selection
+            self.agent_selection = order[0]
+        else:
+            if self._skip_agent_selection is not None:
+                self.agent_selection = self._skip_agent_selection
+            self._skip_agent_selection = None
+        self._clear_rewards()
+
+    def render(self, mode="human"):
+        if mode == "human":
+            print(self.env.export(self.index, 1)[0].render_table())
+
+    def close(self):
+        pass
+
+
+def env(**config):
+    """Drop-in for `rlskyjo.environment.skyjo_env.env(**config)` (skyjo_env.py:19-26): one game on
+    cuda:0 with the reference's keyword arguments (`num_players`, `score_penalty`,
+    `observe_other_player_indirect`, `mean_reward`, `reward_refunded`)."""
+    from .env import BatchedSkyjoEnv
+    device = config.pop("device", "cuda:0")
+    seed = config.pop("seed", 0)
+    return SkyjoAECView(BatchedSkyjoEnv(num_envs=1, auto_reset=False, device=device, seed=seed, **config), 0)
+
+
+def simple_episode(config, policy=None, rng=None, verbose=0):
+    """The reference's canonical consumer loop (vanilla_env_example.py:6-41) on the GPU env.
+    Returns the list of (agent, cumulative reward) seen with done=True."""
+    from .policy import policy_ra
+    e = env(**config)
+    e.reset()
+    finished = []
+    for agent in e.agent_iter(max_iter=300 * config["num_players"]):
+        obs, reward, done, info = e.last()
+        if not done:
+            action = (policy or policy_ra)(obs["observations"], obs["action_mask"], rng)
+            e.step(action)
+            if verbose:
+                e.render()
+        else:
+            e.step(None)
+            finished.append((agent, reward))
+    return finished

@@ -56,7 +56,7 @@
 namespace skyjo {
 
 #ifndef SKYJO_TILE
-#define SKYJO_TILE 64
+#define SKYJO_TILE 32
 #endif
 constexpr int TILE = SKYJO_TILE;  // envs per CTA of the step / observe kernels (32, 64 or 128)
 constexpr int ENV_PAD = 128;      // the env dimension of every plane is padded to a multiple of this

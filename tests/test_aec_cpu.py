@@ -1,0 +1,76 @@
+"""AEC bookkeeping of skyjo_rl_b200.aec.SkyjoAECView (the reference's consumer loop,
+rlskyjo/environment/vanilla_env_example.py:14-35) on the host-compiled backend, checked against
+the oracle playing the same injected game: every live agent sees the oracle's observation, the
+game-over step hands each agent its final reward exactly once with done=True in `agents` order,
+and the dead-step phase empties `agents` (PettingZoo 1.14 semantics)."""
+import numpy as np
+import pytest
+
+from hostsim.sim import HostSimEnv
+from oracle import oracle as O
+from skyjo_rl_b200.aec import SkyjoAECView
+from skyjo_rl_b200.policy import policy_ra
+
+
+class _Backend(HostSimEnv):
+    def observation_space(self, agent):
+        return None
+
+    def action_space(self, agent):
+        return None
+
+
+@pytest.mark.parametrize("N,indirect,mr,rr", [(2, False, 1.0, 0.0), (3, True, 1.0, 0.001), (5, False, 0.0, 0.01)])
+def test_aec_episode_matches_oracle(N, indirect, mr, rr):
+    seed, env_id = 77, 5
+    be = _Backend(num_envs=1, num_players=N, observe_other_player_indirect=indirect, mean_reward=mr,
+                  reward_refunded=rr, seed=seed, auto_reset=False, first_global_env_id=env_id)
+    aec = SkyjoAECView(be, 0)
+    aec.reset()
+    g = O.OracleGame(N, 2.0, indirect)
+    g.reset_rng(seed, env_id, 0)
+    rng = np.random.default_rng(3)
+    seen_done, steps, over = [], 0, False
+    for agent in aec.agent_iter(max_iter=300 * N):
+        obs, reward, done, info = aec.last()
+        if not done:
+            pid = g.expected_action[0]
+            assert agent == f"player_{pid}" and not over
+            o, m = g.collect_observation(pid)
+            np.testing.assert_array_equal(obs["observations"], o)
+            np.testing.assert_array_equal(obs["action_mask"], m)
+            assert reward == 0
+            a = policy_ra(obs["observations"], obs["action_mask"], rng)
+            over = g.act(pid, a)
+            aec.step(a)
+            steps += 1
+        else:
+            seen_done.append((agent, reward))
+            aec.step(None)
+    assert over and not aec.agents
+    exp = g.final_rewards(mr, rr)
+    assert [a for a, _ in seen_done] == [f"player_{i}" for i in range(N)]      # first done agent first
+    assert np.array([r for _, r in seen_done]).tobytes() == exp.tobytes()
+    with pytest.raises(Exception):
+        aec.last()
+
+
+def test_aec_illegal_action_terminates():
+    # TerminateIllegalWrapper(illegal_reward=-1), reference skyjo_env.py:23
+    be = _Backend(num_envs=1, num_players=3, seed=1, auto_reset=False)
+    aec = SkyjoAECView(be, 0)
+    aec.reset()
+    offender = aec.agent_selection
+    aec.step(3)                                  # a place action in the draw phase
+    assert all(aec.dones.values())
+    got = {}
+    for agent in aec.agent_iter():
+        _, reward, done, _ = aec.last()
+        assert done
+        got[agent] = reward
+        with pytest.raises(ValueError):
+            aec.step(5)                          # only None is valid for a done agent
+        aec.step(None)
+    assert got == {a: (-1.0 if a == offender else 0.0) for a in aec.possible_agents}
+    with pytest.raises(AssertionError):
+        SkyjoAECView(be, 0).step(24)             # OrderEnforcingWrapper: reset first
