@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -219,6 +220,7 @@ static StepParams make_params(const SkyjoHandle *h) {
     p.auto_reset = h->cfg.auto_reset;
     p.max_steps = h->cfg.max_episode_steps;
     p.bulk_ok = h->bulk_ok;
+    p.pdl = getenv("SKYJO_NO_PDL") ? 0 : 1;
     return p;
 }
 

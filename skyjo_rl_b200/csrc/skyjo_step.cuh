@@ -48,7 +48,7 @@ __device__ __forceinline__ void store_warp_slice(const uint8_t *s_src, int8_t *g
 }
 
 template <int N, bool IND, bool POLICY>
-__global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __grid_constant__ StepParams p) {
     using OW = ObsWords<N, IND>;
     constexpr int D = OW::D;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -63,6 +63,10 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const Step
     // Warps never wait for each other: each owns its 32 rows of the tile, its stat counters and
     // its own TMA stores, so a warp stalled on a deck byte does not hold back the other three.
     s_stats[warp][lane] = 0;
+    // Programmatic dependent launch: this grid may start while the previous step's grid drains;
+    // nothing it wrote may be read before griddepcontrol.wait (no-ops without the launch attribute).
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
     Env<N> s;
     load_env<N>(p.st.planes, p.Bpad, e, s);  // planes are padded to Bpad: in bounds for every thread

@@ -16,14 +16,23 @@ cudaError_t SKYJO_CAT(launch_step_, SKYJO_N)(const StepParams &p, bool indirect,
     constexpr int N = SKYJO_N;
     const dim3 grid((unsigned)(p.Bpad / TILE)), block(TILE);
     const size_t smem = (size_t)TILE * ((indirect ? 31 : 19 + 12 * N) + 26);
+    // programmatic stream serialization: the grid may be scheduled while its predecessor drains
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (indirect) {
-        if (policy) step_kernel<N, true, true><<<grid, block, smem, s>>>(p);
-        else step_kernel<N, true, false><<<grid, block, smem, s>>>(p);
-    } else {
-        if (policy) step_kernel<N, false, true><<<grid, block, smem, s>>>(p);
-        else step_kernel<N, false, false><<<grid, block, smem, s>>>(p);
+        if (policy) return cudaLaunchKernelEx(&cfg, step_kernel<N, true, true>, p);
+        return cudaLaunchKernelEx(&cfg, step_kernel<N, true, false>, p);
     }
-    return cudaGetLastError();
+    if (policy) return cudaLaunchKernelEx(&cfg, step_kernel<N, false, true>, p);
+    return cudaLaunchKernelEx(&cfg, step_kernel<N, false, false>, p);
 }
 
 cudaError_t SKYJO_CAT(launch_observe_, SKYJO_N)(const StepParams &p, bool indirect, int agent, int8_t *obs,
