@@ -64,9 +64,16 @@ class SkyjoAECView:
     def seed(self, seed=None):
         if seed is not None:
             self.env.seed(seed)
-            self.reset_after_seed()
+            self._begin_episode()
 
-    def reset_after_seed(self):
+    def reset_injected(self, deck, flips):
+        """reset() with the deck order (int8[150]) and the open slots (uint8[N,2]) supplied instead
+        of shuffled: replays a recorded game.  Single-env backends only."""
+        assert self.env.num_envs == 1
+        self.env.reset_injected(np.asarray(deck, np.int8)[None], np.asarray(flips, np.uint8)[None])
+        self._begin_episode()
+
+    def _begin_episode(self):
         self.agents = self.possible_agents[:]
         self.rewards = {a: 0 for a in self.agents}
         self._cumulative_rewards = {a: 0 for a in self.agents}

@@ -7,7 +7,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    # n<players>_*.npz: per-config fixtures from make_golden.py (notebook_trace.npz has its own test)
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f[0] == "n" and f[1].isdigit())
 
 
 class Golden:

@@ -69,3 +69,35 @@ def test_action_mask_policy_rollout_is_zero_copy_and_legal():
     assert bool(torch.isfinite(pol.value_function()).all())
     assert bool((logits[env.action_mask == 0] < -1e30).all())
     env.check()
+
+
+def test_gpu_aec_replays_notebook_trace():
+    # the reference's recorded episode (notebooks/trainpettingzoo.ipynb cell 5) through the CUDA env
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    from skyjo_rl_b200.aec import SkyjoAECView
+    from test_notebook_trace import load_trace, replay_through_aec
+    env = BatchedSkyjoEnv(num_envs=1, num_players=3, score_penalty=2.0, mean_reward=1.0, reward_refunded=0.0,
+                          auto_reset=False)
+    replay_through_aec(SkyjoAECView(env, 0), load_trace())
+    v = env.game_view(0)
+    assert v.is_terminated and "u1" in v.render_table()          # the one card that stayed hidden (value 1)
+
+
+def test_checkpoint_restore_resumes_bit_identically():
+    # env-state checkpoint / resume
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    kw = dict(num_envs=3000, num_players=4, seed=99, reward_refunded=0.01)
+    a = BatchedSkyjoEnv(**kw)
+    a.reset()
+    a.step_random(203)
+    sd = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in a.state_dict().items()}
+    a.step_random(150)
+    b = BatchedSkyjoEnv(**kw)
+    b.reset()
+    b.load_state_dict({k: (v.to(b.device) if torch.is_tensor(v) else v) for k, v in sd.items()})
+    b.step_random(150)
+    assert torch.equal(a.observations, b.observations) and torch.equal(a.action_mask, b.action_mask)
+    assert torch.equal(a.rewards, b.rewards) and torch.equal(a.done_code, b.done_code)
+    assert torch.equal(a.agent_selection, b.agent_selection)
+    a.check()
+    b.check()
