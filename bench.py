@@ -355,12 +355,18 @@ def run_e2e(args, env, dev, rank, world):
     dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    illegal = e.stats()["illegal"]
+    st = e.stats()
     e.check()
-    assert illegal == 0, "replayed actions must be legal"
+    assert st["illegal"] == 0, "replayed actions must be legal"
+    # bytes that cross the link per step (csrc/skyjo_hostio.cuh): obs rows as they are, mask + agent + done as
+    # one packed word per env, a 4-byte count, and one {env, N rewards} entry per episode that ended
+    ended_per_step = (st["episodes"] + st["truncated"]) / float(T + Tw)
+    d2h = B * (D + 4) + 4 + int(ended_per_step * (8 + 8 * N))
     return {"value": B * world * T / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": B,
-            "d2h_bytes_per_step": B * (D + 26 + 1 + 1 + 8 * N), "steps": T,
-            "api": "skyjo_step_host (C ABI) via BatchedSkyjoEnv.step_host, pinned host buffers"}
+            "d2h_bytes_per_step": d2h, "steps": T,
+            "host_buffer_bytes_filled_per_step": B * (D + 26 + 1 + 1 + 8 * N),
+            "api": "skyjo_step_host (C ABI) via BatchedSkyjoEnv.step_host, pinned host buffers: obs int8[B,D], "
+                   "mask int8[B,26], agent, done, reward f64[B,N] all filled every step"}
 
 
 def main():

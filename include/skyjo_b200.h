@@ -166,11 +166,21 @@ int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream);
  * Measurement aid for bench.py's roofline figure. */
 int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double *step_ms,
                               double *deal_ms, int64_t *n_step_launches, int64_t *n_deal_launches);
-/* Host-buffer entry for end-to-end use: copies actions (uint8[B]) to the device, steps,
- * copies obs / mask / agent / done / reward back; synchronises.  Null outputs are skipped. */
+/* Host-buffer entry for end-to-end use (env.step(a); env.last() of vanilla_env_example.py:14-35
+ * for every env): copies actions (uint8[B]) to the device, steps, and fills the host buffers
+ * obs int8[B,D] / mask int8[B,26] / agent int8[B] / done uint8[B] / reward float64[B,N] with
+ * exactly what the device output buffers hold.  Null outputs are skipped.  Returns when the host
+ * buffers are complete (the refill deal of finished envs may still be running on `stream`).
+ * Wire format (csrc/skyjo_hostio.cuh): mask + agent + done cross the link as one 32-bit word per
+ * env and are expanded on the host by a few worker threads; reward rows cross only for envs
+ * whose episode ended in this step, the other rows are zero-filled on the host.  Use pinned
+ * host buffers for full link speed, and the same reward buffer on consecutive calls. */
 int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host,
                     int8_t *mask_host, int8_t *agent_host, uint8_t *done_host,
                     double *reward_host, void *stream);
+/* worker threads skyjo_step_host uses for the host-side expansion; 0 = default
+ * (min(4, hardware threads / LOCAL_WORLD_SIZE), or SKYJO_HOST_THREADS) */
+int skyjo_set_host_threads(SkyjoHandle *h, int n);
 
 /* SimpleSkyjoEnv.observe(agent) (skyjo_env.py:199-214) for an arbitrary seat; agent = -1
  * means each env's agent_selection.  Writes int8[B,D] / int8[B,26]. */
@@ -201,6 +211,11 @@ void skyjo_host_deck(uint64_t seed, uint64_t global_env, uint32_t episode, int8_
 void skyjo_host_flips(uint64_t seed, uint64_t global_env, uint32_t episode, int num_players,
                       uint8_t *out /* [N][2] */);
 int skyjo_host_policy(uint64_t seed, uint64_t global_env, uint64_t t, uint32_t legal_bits);
+/* Host half of skyjo_step_host's wire format: expands n packed words (bits 0..25 legal actions,
+ * 26..27 done code, 28..31 agent) into mask int8[n,26] / agent int8[n] / done uint8[n]
+ * (null outputs are skipped). */
+void skyjo_host_expand_packed(const uint32_t *packed, int64_t n, int8_t *mask, int8_t *agent,
+                              uint8_t *done);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libskyjo_b200.so")
+# SKYJO_LIB: development override used by tools/variants.py to time experimental builds of the same
+# library side by side; the product always loads the in-tree libskyjo_b200.so
+LIB_PATH = os.environ.get("SKYJO_LIB") or os.path.join(HERE, "libskyjo_b200.so")
 
 MAX_PLAYERS = 12
 NUM_ACTIONS = 26
@@ -27,10 +29,10 @@ STAT_NAMES = [
 EXPORTS = [
     "skyjo_abi_version", "skyjo_last_error", "skyjo_obs_len", "skyjo_state_bytes", "skyjo_create",
     "skyjo_destroy", "skyjo_bind_outputs", "skyjo_reset", "skyjo_reset_injected", "skyjo_seed",
-    "skyjo_step", "skyjo_step_random", "skyjo_step_random_profile", "skyjo_step_host", "skyjo_observe", "skyjo_stats_device",
+    "skyjo_step", "skyjo_step_random", "skyjo_step_random_profile", "skyjo_step_host", "skyjo_set_host_threads", "skyjo_observe", "skyjo_stats_device",
     "skyjo_stats_host", "skyjo_stats_clear", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
     "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
-    "skyjo_host_policy",
+    "skyjo_host_policy", "skyjo_host_expand_packed",
 ]
 
 
@@ -113,6 +115,7 @@ def load():
         "skyjo_step_random_profile": (i32, [vp, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                              C.POINTER(i64), C.POINTER(i64)]),
         "skyjo_step_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "skyjo_set_host_threads": (i32, [vp, i32]),
         "skyjo_observe": (i32, [vp, i32, vp, vp, vp]),
         "skyjo_stats_device": (i32, [vp, vp, vp]),
         "skyjo_stats_host": (i32, [vp, vp, vp]),
@@ -126,6 +129,7 @@ def load():
         "skyjo_host_deck": (None, [u64, u64, u32, vp]),
         "skyjo_host_flips": (None, [u64, u64, u32, i32, vp]),
         "skyjo_host_policy": (i32, [u64, u64, u64, u32]),
+        "skyjo_host_expand_packed": (None, [vp, i64, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

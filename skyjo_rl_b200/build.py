@@ -51,6 +51,25 @@ def build(force=False, verbose=False):
     jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(OBJ, "skyjo_capi.o"), [])]
     for n in range(1, 13):
         jobs.append((os.path.join(CSRC, "skyjo_step_inst.cu"), os.path.join(OBJ, f"skyjo_step_n{n}.o"), [f"-DSKYJO_N={n}"]))
+    return _run(jobs, LIB, verbose)
+
+
+def build_variant(out, defines=(), players=(4,), verbose=False):
+    """Development aid (tools/variants.py): an experimental build of the library with extra -D
+    flags, only the listed player counts instantiated (the others fail with SKYJO_E_INVALID)."""
+    tag = os.path.splitext(os.path.basename(out))[0]
+    obj = os.path.join(OBJ, "variants", tag)
+    os.makedirs(obj, exist_ok=True)
+    os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
+    dflags = [f"-D{d}" for d in defines]
+    mask = sum(1 << (n - 1) for n in players)
+    jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(obj, "skyjo_capi.o"), dflags + [f"-DSKYJO_ONLY_PLAYERS_MASK={mask}"])]
+    for n in players:
+        jobs.append((os.path.join(CSRC, "skyjo_step_inst.cu"), os.path.join(obj, f"skyjo_step_n{n}.o"), dflags + [f"-DSKYJO_N={n}"]))
+    return _run(jobs, out, verbose)
+
+
+def _run(jobs, LIB, verbose):
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(_compile, jobs))
     cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]

@@ -8,19 +8,28 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <new>
 #include <vector>
 
 #include "../../include/skyjo_b200.h"
 #include "skyjo_deal.cuh"
+#include "skyjo_hostio.cuh"
 #include "skyjo_rng.cuh"
 #include "skyjo_state.cuh"
 #include "skyjo_step.cuh"
 
 namespace skyjo {
+// development builds (build.build_variant) instantiate only some player counts: the others stay
+// undefined weak symbols (null) and skyjo_create rejects them
+#ifdef SKYJO_ONLY_PLAYERS_MASK
+#define SKYJO_WEAK __attribute__((weak))
+#else
+#define SKYJO_WEAK
+#endif
 #define SKYJO_DECL(n)                                                                                     \
-    cudaError_t launch_step_##n(const StepParams &, bool, bool, cudaStream_t);                            \
-    cudaError_t launch_observe_##n(const StepParams &, bool, int, int8_t *, int8_t *, int, int, cudaStream_t);
+    SKYJO_WEAK cudaError_t launch_step_##n(const StepParams &, bool, bool, cudaStream_t);                 \
+    SKYJO_WEAK cudaError_t launch_observe_##n(const StepParams &, bool, int, int8_t *, int8_t *, int, int, cudaStream_t);
 SKYJO_DECL(1) SKYJO_DECL(2) SKYJO_DECL(3) SKYJO_DECL(4) SKYJO_DECL(5) SKYJO_DECL(6)
 SKYJO_DECL(7) SKYJO_DECL(8) SKYJO_DECL(9) SKYJO_DECL(10) SKYJO_DECL(11) SKYJO_DECL(12)
 #undef SKYJO_DECL
@@ -34,6 +43,10 @@ static const observe_launch_fn kObserve[SKYJO_MAX_PLAYERS] = {
 }  // namespace skyjo
 
 using namespace skyjo;
+
+#ifndef SKYJO_DEFAULT_PF_DIST
+#define SKYJO_DEFAULT_PF_DIST 1184
+#endif
 
 struct SkyjoHandle {
     SkyjoConfig cfg;
@@ -49,10 +62,25 @@ struct SkyjoHandle {
     long long launches;
     int steps_since_deal;
     int obs_len;
+    int pf_dist;  // L2 prefetch distance of the step kernel, in tiles
     // optional per-kernel event timing (skyjo_step_random_profile)
     bool profiling;
     std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
     std::vector<int> prof_kind;            // 0 step kernel, 1 deal kernel
+    // skyjo_step_host wire staging (skyjo_hostio.cuh), created on first use
+    bool hostio_ready;
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_packed_ready, ev_small_done, ev_all_done;
+    uint32_t *packed_dev, *packed_host;     // [B]
+    unsigned int *counter_dev, *counter_host;
+    double *entries_host, *entries_dev;     // host-mapped pinned, [cap][1 + N]
+    unsigned int sparse_cap;
+    int host_threads;
+    HostPool *pool;
+    double trace_us[6];                     // SKYJO_HOSTIO_TRACE: enqueue, wait small, expand, scatter, wait all
+    long long trace_calls;
+    const double *last_reward_host;         // buffer whose non-zero rows are tracked
+    std::vector<long long> last_reward_rows;
 };
 
 static void prof_begin(SkyjoHandle *h, int kind, cudaStream_t s) {
@@ -140,6 +168,8 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
         return fail(SKYJO_E_NO_DEVICE, "no CUDA device: libskyjo_b200 has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return fail(SKYJO_E_INVALID, "bad device index");
+    if (!kStep[cfg->num_players - 1] || !kObserve[cfg->num_players - 1])
+        return fail(SKYJO_E_INVALID, "this development build does not instantiate that player count");
     const Layout L = layout_for(cfg->num_players, num_envs);
     if (!state_dev || state_bytes < L.total || ((uintptr_t)state_dev & 255)) {
         return fail(SKYJO_E_INVALID, "state buffer null, too small or not 256-byte aligned");
@@ -173,6 +203,14 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     h->steps_since_deal = 0;
     h->obs_len = skyjo_obs_len(cfg);
     h->profiling = false;
+    h->hostio_ready = false;
+    h->pool = nullptr;
+    h->host_threads = 0;
+    h->last_reward_host = nullptr;
+    h->trace_calls = 0;
+    for (double &v : h->trace_us) v = 0.0;
+    h->pf_dist = SKYJO_DEFAULT_PF_DIST;
+    if (const char *g = getenv("SKYJO_PF_DIST")) h->pf_dist = atoi(g);  // experiment knob
     cudaError_t e = cudaMemset(state_dev, 0, (size_t)L.total);
     if (e != cudaSuccess) {
         delete h;
@@ -182,7 +220,32 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     return SKYJO_OK;
 }
 
+static void hostio_release(SkyjoHandle *h) {
+    if (h->trace_calls && getenv("SKYJO_HOSTIO_TRACE")) {
+        const double n = (double)h->trace_calls;
+        fprintf(stderr, "[skyjo_step_host] %lld calls, mean us: enqueue %.1f | wait packed %.1f | expand %.1f | "
+                        "scatter rewards %.1f | wait obs %.1f\n", h->trace_calls, h->trace_us[0] / n, h->trace_us[1] / n,
+                h->trace_us[2] / n, h->trace_us[3] / n, h->trace_us[4] / n);
+    }
+    delete h->pool;
+    h->pool = nullptr;
+    if (!h->hostio_ready) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->copy_stream);
+    cudaFree(h->packed_dev);
+    cudaFree(h->counter_dev);
+    cudaFreeHost(h->packed_host);
+    cudaFreeHost(h->counter_host);
+    cudaFreeHost(h->entries_host);
+    cudaEventDestroy(h->ev_packed_ready);
+    cudaEventDestroy(h->ev_small_done);
+    cudaEventDestroy(h->ev_all_done);
+    cudaStreamDestroy(h->copy_stream);
+    h->hostio_ready = false;
+}
+
 int skyjo_destroy(SkyjoHandle *h) {
+    if (h) hostio_release(h);
     delete h;
     return SKYJO_OK;
 }
@@ -221,6 +284,7 @@ static StepParams make_params(const SkyjoHandle *h) {
     p.max_steps = h->cfg.max_episode_steps;
     p.bulk_ok = h->bulk_ok;
     p.pdl = getenv("SKYJO_NO_PDL") ? 0 : 1;
+    p.pf_dist = h->pf_dist;
     return p;
 }
 
@@ -368,24 +432,137 @@ int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double 
     return SKYJO_OK;
 }
 
+static int default_host_threads() {
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    int ranks = 1;  // ranks sharing this host under torchrun
+    if (const char *g = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(g) > 0 ? atoi(g) : 1;
+    int n = hw / ranks;
+    if (const char *g = getenv("SKYJO_HOST_THREADS")) n = atoi(g);
+    return n < 1 ? 1 : (n > 4 && !getenv("SKYJO_HOST_THREADS") ? 4 : (n > 64 ? 64 : n));
+}
+
+int skyjo_set_host_threads(SkyjoHandle *h, int n) {
+    if (!h || n < 0 || n > 64) return fail(SKYJO_E_INVALID, "host threads must be 0 (default) .. 64");
+    h->host_threads = n;
+    delete h->pool;
+    h->pool = nullptr;
+    return SKYJO_OK;
+}
+
+static int hostio_init(SkyjoHandle *h) {
+    if (h->hostio_ready) return SKYJO_OK;
+    const size_t B = (size_t)h->B, N = (size_t)h->cfg.num_players;
+    h->sparse_cap = (unsigned int)(B / 8 > 64 ? B / 8 : 64);
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_packed_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_small_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_all_done, cudaEventDisableTiming));
+    CU(cudaMalloc(&h->packed_dev, B * 4));
+    CU(cudaMalloc(&h->counter_dev, 4));
+    CU(cudaHostAlloc(&h->packed_host, B * 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&h->counter_host, 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&h->entries_host, (size_t)h->sparse_cap * (1 + N) * 8, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer(&h->entries_dev, h->entries_host, 0));
+    h->hostio_ready = true;
+    return SKYJO_OK;
+}
+
 int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host, int8_t *mask_host,
                     int8_t *agent_host, uint8_t *done_host, double *reward_host, void *stream) {
     if (!h || !actions_host) return fail(SKYJO_E_INVALID, "null argument");
     if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
     CU(cudaSetDevice(h->device));
-    cudaStream_t s = (cudaStream_t)stream;
+    int rc = hostio_init(h);
+    if (rc) return rc;
+    if (!h->pool) h->pool = new (std::nothrow) HostPool(h->host_threads > 0 ? h->host_threads : default_host_threads());
+    if (!h->pool) return fail(SKYJO_E_INVALID, "out of host memory");
+    cudaStream_t s = (cudaStream_t)stream, cs = h->copy_stream;
+    const size_t B = (size_t)h->B, N = (size_t)h->cfg.num_players;
+    using clk = std::chrono::steady_clock;
+    auto t_prev = clk::now();
+    auto lap = [&](int k) {
+        const auto now = clk::now();
+        h->trace_us[k] += std::chrono::duration<double, std::micro>(now - t_prev).count();
+        t_prev = now;
+    };
     // the agent buffer doubles as the staging area of the uint8 actions: it is rewritten by the step
     uint8_t *act_dev = (uint8_t *)h->outs.agent_dev;
-    CU(cudaMemcpyAsync(act_dev, actions_host, (size_t)h->B, cudaMemcpyHostToDevice, s));
-    int rc = step_once(h, act_dev, SKYJO_ACT_U8, false, s);
-    if (rc) return rc;
-    const size_t B = (size_t)h->B, N = (size_t)h->cfg.num_players;
-    if (obs_host) CU(cudaMemcpyAsync(obs_host, h->outs.obs_dev, B * (size_t)h->obs_len, cudaMemcpyDeviceToHost, s));
-    if (mask_host) CU(cudaMemcpyAsync(mask_host, h->outs.action_mask_dev, B * 26, cudaMemcpyDeviceToHost, s));
-    if (agent_host) CU(cudaMemcpyAsync(agent_host, h->outs.agent_dev, B, cudaMemcpyDeviceToHost, s));
-    if (done_host) CU(cudaMemcpyAsync(done_host, h->outs.done_dev, B, cudaMemcpyDeviceToHost, s));
-    if (reward_host) CU(cudaMemcpyAsync(reward_host, h->outs.reward_dev, B * N * 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    CU(cudaMemcpyAsync(act_dev, actions_host, B, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(h->counter_dev, 0, 4, s));
+    // step kernel only; the refill deal is queued after the pack kernel so that it overlaps the copies
+    StepParams p = make_params(h);
+    p.actions = act_dev;
+    p.action_dtype = SKYJO_ACT_U8;
+    CU(kStep[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, false, s));
+    h->launches += 1;
+    h->t += 1;
+    const bool want_small = mask_host || agent_host || done_host || reward_host;
+    if (want_small) {
+        pack_host_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(
+            h->st.planes, h->Bpad, h->B, (int)N, (const uint8_t *)h->outs.done_dev, (const double *)h->outs.reward_dev,
+            h->packed_dev, h->counter_dev, reward_host ? h->entries_dev : nullptr, h->sparse_cap);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(h->ev_packed_ready, s));
+    if (h->cfg.auto_reset) {  // external actions may end any episode at once: refill after every step
+        h->steps_since_deal = 0;
+        rc = launch_deal(h, 1, 1, nullptr, nullptr, s);
+        if (rc) return rc;
+    }
+    CU(cudaStreamWaitEvent(cs, h->ev_packed_ready, 0));
+    if (want_small) {
+        CU(cudaMemcpyAsync(h->packed_host, h->packed_dev, B * 4, cudaMemcpyDeviceToHost, cs));
+        CU(cudaMemcpyAsync(h->counter_host, h->counter_dev, 4, cudaMemcpyDeviceToHost, cs));
+        CU(cudaEventRecord(h->ev_small_done, cs));
+    }
+    if (obs_host) CU(cudaMemcpyAsync(obs_host, h->outs.obs_dev, B * (size_t)h->obs_len, cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(h->ev_all_done, cs));
+    lap(0);
+
+    if (want_small) {
+        // previous call's reward rows back to zero while the packed words travel
+        if (reward_host) {
+            if (h->last_reward_host != reward_host) {
+                memset(reward_host, 0, B * N * 8);
+                h->last_reward_host = reward_host;
+            } else {
+                for (long long e : h->last_reward_rows) memset(reward_host + (size_t)e * N, 0, N * 8);
+            }
+            h->last_reward_rows.clear();
+        }
+        CU(cudaEventSynchronize(h->ev_small_done));
+        lap(1);
+        const uint32_t *packed = h->packed_host;
+        const long long nB = h->B;
+        h->pool->run([=](int part, int parts) {
+            const long long e0 = nB * part / parts, e1 = nB * (part + 1) / parts;
+            expand_packed(packed, e0, e1, mask_host, agent_host, done_host);
+        });
+        lap(2);
+        if (reward_host) {
+            const unsigned int cnt = *h->counter_host;
+            if (cnt <= h->sparse_cap) {
+                // the pack kernel finished before ev_small_done: its writes to the mapped buffer are visible
+                for (unsigned int i = 0; i < cnt; ++i) {
+                    const double *src = h->entries_host + (size_t)i * (1 + N);
+                    const long long e = (long long)reinterpret_cast<const unsigned long long *>(src)[0];
+                    memcpy(reward_host + (size_t)e * N, src + 1, N * 8);
+                    h->last_reward_rows.push_back(e);
+                }
+            } else {
+                // more finished envs than the compact buffer holds: dense copy of the reward tensor
+                CU(cudaMemcpyAsync(reward_host, h->outs.reward_dev, B * N * 8, cudaMemcpyDeviceToHost, cs));
+                CU(cudaEventRecord(h->ev_all_done, cs));
+                h->last_reward_host = nullptr;  // every row may be non-zero: start from a memset next time
+            }
+        }
+    }
+    lap(3);
+    CU(cudaEventSynchronize(h->ev_all_done));
+    lap(4);
+    h->trace_calls += 1;
     return SKYJO_OK;
 }
 
@@ -493,6 +670,10 @@ void skyjo_host_flips(uint64_t seed, uint64_t genv, uint32_t episode, int num_pl
         out[2 * q] = (uint8_t)a;
         out[2 * q + 1] = (uint8_t)b;
     }
+}
+
+void skyjo_host_expand_packed(const uint32_t *packed, int64_t n, int8_t *mask, int8_t *agent, uint8_t *done) {
+    expand_packed(packed, 0, n, mask, agent, done);
 }
 
 int skyjo_host_policy(uint64_t seed, uint64_t genv, uint64_t t, uint32_t legal_bits) {

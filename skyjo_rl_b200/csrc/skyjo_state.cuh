@@ -253,6 +253,7 @@ struct StepParams {
     int auto_reset, max_steps;
     int bulk_ok;  // obs / mask base pointers 16-byte aligned -> TMA bulk stores
     int pdl;      // host side: launch with programmatic stream serialization
+    int pf_dist;  // step kernel: L2 prefetch distance in tiles (0 = off)
 };
 
 enum : uint32_t { ERR_NEXT_NOT_READY = 1, ERR_BAD_DECK = 2, ERR_BAD_FLIPS = 4 };

@@ -31,6 +31,74 @@ namespace skyjo {
 
 constexpr int WARPS = TILE / 32;
 
+// ---- L2 residency hints -------------------------------------------------------------------------
+// The live planes of 2^20 4-player envs are 84 MB, the outputs of one step 100 MB, the L2 126 MB.
+// Without hints the output stream evicts the planes between two steps and every step re-reads
+// them from DRAM.  SKYJO_L2_KEEP marks plane loads / stores evict_last, SKYJO_L2_STREAM marks the
+// output stores evict_first, so that the state stays L2-resident across steps when it fits.
+#ifndef SKYJO_L2_KEEP
+#define SKYJO_L2_KEEP 0
+#endif
+#ifndef SKYJO_L2_STREAM
+#define SKYJO_L2_STREAM 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ U128 ld128_hint(const U128 *p, uint64_t pol) {
+    U128 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st128_hint(U128 *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(x), "r"(y), "r"(z),
+                 "r"(w), "l"(pol)
+                 : "memory");
+}
+template <int N>
+__device__ __forceinline__ void load_env_dev(const U128 *planes, long long Bpad, long long e, Env<N> &s) {
+#if SKYJO_L2_KEEP
+    const uint64_t pol = l2_policy_keep();
+    const U128 P0 = ld128_hint(planes + e, pol);
+    s.hdr = pack64(P0.x, P0.y);
+    s.hist = pack64(P0.z, P0.w);
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const U128 T = ld128_hint(planes + (long long)(1 + q) * Bpad + e, pol);
+        s.row[q].w0 = T.x;
+        s.row[q].w1 = T.y;
+        s.row[q].w2 = T.z;
+        s.row[q].w3 = T.w;
+    }
+#else
+    load_env<N>(planes, Bpad, e, s);
+#endif
+}
+template <int N>
+__device__ __forceinline__ void store_env_dev(U128 *planes, long long Bpad, long long e, const Env<N> &s,
+                                              uint32_t dirty_rows, uint32_t pf_new) {
+#if SKYJO_L2_KEEP
+    const uint64_t pol = l2_policy_keep();
+    const uint64_t hdr = pf_new == 0xFFFFFFFFu ? s.hdr : hdr_pf_set(s.hdr, pf_new);
+    st128_hint(planes + e, (uint32_t)hdr, (uint32_t)(hdr >> 32), (uint32_t)s.hist, (uint32_t)(s.hist >> 32), pol);
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+        if ((dirty_rows >> q) & 1u)
+            st128_hint(planes + (long long)(1 + q) * Bpad + e, s.row[q].w0, s.row[q].w1, s.row[q].w2, s.row[q].w3, pol);
+#else
+    store_env<N>(planes, Bpad, e, s, dirty_rows, pf_new);
+#endif
+}
+
 // Stores one warp's 32-row slice of an output tile: one TMA bulk store issued by lane 0 when the
 // slice is complete and 16-byte aligned, a byte loop otherwise (ragged last tile).
 __device__ __forceinline__ void store_warp_slice(const uint8_t *s_src, int8_t *g_dst, uint32_t row_bytes,
@@ -38,9 +106,16 @@ __device__ __forceinline__ void store_warp_slice(const uint8_t *s_src, int8_t *g
     if (bulk_ok && rows_valid == 32u) {
         if (lane == 0) {
             const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(s_src);
+#if SKYJO_L2_STREAM
+            const uint64_t pol = l2_policy_stream();
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(g_dst),
+                         "r"(saddr), "r"(32u * row_bytes), "l"(pol)
+                         : "memory");
+#else
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(g_dst),
                          "r"(saddr), "r"(32u * row_bytes)
                          : "memory");
+#endif
         }
     } else {
         for (uint32_t i = lane; i < rows_valid * row_bytes; i += 32u) g_dst[i] = (int8_t)s_src[i];
@@ -66,10 +141,24 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     // Programmatic dependent launch: this grid may start while the previous step's grid drains;
     // nothing it wrote may be read before griddepcontrol.wait (no-ops without the launch attribute).
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    // L2 prefetch of the planes of the tile `pf_dist` CTAs ahead (about one wave of resident CTAs):
+    // by the time that CTA is scheduled its 1 + N plane loads hit L2 instead of waiting for DRAM.
+    // One bulk-prefetch instruction per plane (512 B = the tile's slice), issued by lane 0.
+    if (p.pf_dist > 0 && lane == 0) {
+        const long long pt = (long long)blockIdx.x + p.pf_dist;
+        if (pt < (long long)gridDim.x) {
+            const U128 *src = p.st.planes + pt * TILE;
+#pragma unroll
+            for (int q = 0; q <= N; ++q)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src + (long long)q * p.Bpad),
+                             "r"((uint32_t)(TILE * 16))
+                             : "memory");
+        }
+    }
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
     Env<N> s;
-    load_env<N>(p.st.planes, p.Bpad, e, s);  // planes are padded to Bpad: in bounds for every thread
+    load_env_dev<N>(p.st.planes, p.Bpad, e, s);  // planes are padded to Bpad: in bounds for every thread
     int action = 0;
     if (!POLICY && valid) action = load_action(p.actions, p.action_dtype, e);
     __syncwarp();
@@ -115,7 +204,7 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     // state write-back after the staging: a draw-pile prefetch issued by env_step has had the
     // whole encode to arrive before the header is stored
     if (valid) {
-        store_env<N>(p.st.planes, p.Bpad, e, s, dirty_rows, pf_new);
+        store_env_dev<N>(p.st.planes, p.Bpad, e, s, dirty_rows, pf_new);
         p.agent[e] = (int8_t)((s.hdr >> HDR_CUR_SH) & 0xF);
         p.done[e] = (uint8_t)done_code;
     }

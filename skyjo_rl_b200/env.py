@@ -204,6 +204,10 @@ class BatchedSkyjoEnv:
         _lib.check(self._L.skyjo_step_host(self._h, ptr(actions), ptr(obs), ptr(mask), ptr(agent), ptr(done),
                                            ptr(reward), self._stream()))
 
+    def set_host_threads(self, n=0):
+        """Worker threads step_host uses to expand the packed mask / agent / done words (0 = default)."""
+        _lib.check(self._L.skyjo_set_host_threads(self._h, int(n)))
+
     def observe(self, agent=None):
         """SimpleSkyjoEnv.observe (skyjo_env.py:199-214).  agent=None returns the live buffers
         (view of each env's agent_selection); a name or index encodes that seat's view."""

@@ -85,3 +85,22 @@ def test_spaces_match_reference_bounds():
     b = Box(low=-24, high=127, shape=(67,), dtype=np.int8)   # reference skyjo_env.py:129-134
     assert b.shape == (67,) and b.low.min() == -24 and b.high.max() == 127
     assert Discrete(26).n == 26                               # skyjo_env.py:146-151
+
+
+def test_host_expand_packed_matches_numpy_unpack():
+    """Host half of skyjo_step_host's wire format (csrc/skyjo_hostio.cuh): one uint32 per env ->
+    mask[26] + agent + done."""
+    L = _lib.load()
+    rng = np.random.default_rng(5)
+    n = 1000
+    packed = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    packed[:4] = [0, 0xFFFFFFFF, 3 << 24, (1 << 26) - 1]
+    mask = np.full((n, 26), 7, np.int8)
+    agent = np.full(n, 7, np.int8)
+    done = np.full(n, 7, np.uint8)
+    L.skyjo_host_expand_packed(packed.ctypes.data, n, mask.ctypes.data, agent.ctypes.data, done.ctypes.data)
+    exp_mask = ((packed[:, None] >> np.arange(26, dtype=np.uint32)[None, :]) & 1).astype(np.int8)
+    np.testing.assert_array_equal(mask, exp_mask)
+    np.testing.assert_array_equal(agent, (packed >> 28).astype(np.int8))
+    np.testing.assert_array_equal(done, ((packed >> 26) & 3).astype(np.uint8))
+    L.skyjo_host_expand_packed(packed.ctypes.data, n, None, None, done.ctypes.data)   # null outputs are skipped
