@@ -161,6 +161,29 @@ int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *
 /* n_steps fused launches with the uniform legal policy (random_admissible_policy.py:26-28)
  * drawn in-kernel: the loop of sample_game.py:10-21. */
 int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream);
+/* Time-major rollout buffers (device) of skyjo_rollout_random: obs int8[T, B, D];
+ * action_mask int8[T, B, 26]; agent int8[T, B]; done uint8[T, B]. */
+typedef struct SkyjoRollout {
+    void *obs_dev;
+    void *action_mask_dev;
+    void *agent_dev;
+    void *done_dev;
+} SkyjoRollout;
+/* The same n_steps env-steps as skyjo_step_random (identical games, statistics and final state),
+ * run as multi-step launches: each kernel advances its envs by up to 8 consecutive env-steps with
+ * the state held in registers and stores what step t would have published -- the next agent's
+ * observation, action mask, agent and done code -- into slice t of the time-major buffers (the
+ * rollout storage a learner consumes, sample_game.py:10-21 unrolled in time).  The bound [B, ...]
+ * outputs receive the last step's values; reward / final_score keep their [B, N] "last finished
+ * episode" meaning (an episode that ends inside a launch is visible in the statistics, its
+ * reward row is cleared by the env's next step as in skyjo_env.py:250-252). */
+int skyjo_rollout_random(SkyjoHandle *h, int n_steps, const SkyjoRollout *out, void *stream);
+/* Per-kernel CUDA-event timing of everything launched between begin and end on `stream`
+ * (summed device ms and launch counts of step / rollout kernels and of deal kernels); end
+ * synchronises.  Measurement aid for bench.py's roofline figure. */
+int skyjo_profile_begin(SkyjoHandle *h);
+int skyjo_profile_end(SkyjoHandle *h, void *stream, double *step_ms, double *deal_ms,
+                      int64_t *n_step_launches, int64_t *n_deal_launches);
 /* skyjo_step_random with every kernel bracketed by CUDA events on `stream`: returns the summed
  * device time (ms) and launch counts of the step kernels and of the deal kernels; synchronises.
  * Measurement aid for bench.py's roofline figure. */
@@ -193,6 +216,9 @@ int skyjo_stats_device(SkyjoHandle *h, int64_t *out_dev, void *stream);
 int skyjo_stats_host(SkyjoHandle *h, int64_t *out_host, void *stream);
 int skyjo_stats_clear(SkyjoHandle *h, void *stream);
 
+/* Closes the running refill window and makes `stream` wait for the library's internal streams:
+ * work queued on `stream` afterwards may read or overwrite the state buffer (checkpointing). */
+int skyjo_quiesce(SkyjoHandle *h, void *stream);
 /* SkyjoGame-shaped dump of envs [env0, env0+count) into out_dev (device memory). */
 int skyjo_export_debug(SkyjoHandle *h, int64_t env0, int64_t count, SkyjoEnvDebug *out_dev,
                        void *stream);
@@ -200,7 +226,7 @@ int skyjo_export_debug(SkyjoHandle *h, int64_t env0, int64_t count, SkyjoEnvDebu
 int skyjo_check(SkyjoHandle *h, void *stream);
 /* lockstep counter (number of step launches since creation / seed) */
 int64_t skyjo_step_count(const SkyjoHandle *h);
-/* restore the lockstep counter when resuming from a saved state buffer */
+/* restore the lockstep counter when resuming from a state buffer saved after skyjo_quiesce */
 int skyjo_set_step_count(SkyjoHandle *h, int64_t t);
 /* kernels launched by this handle so far */
 int64_t skyjo_launch_count(const SkyjoHandle *h);

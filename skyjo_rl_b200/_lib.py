@@ -29,8 +29,9 @@ STAT_NAMES = [
 EXPORTS = [
     "skyjo_abi_version", "skyjo_last_error", "skyjo_obs_len", "skyjo_state_bytes", "skyjo_create",
     "skyjo_destroy", "skyjo_bind_outputs", "skyjo_reset", "skyjo_reset_injected", "skyjo_seed",
-    "skyjo_step", "skyjo_step_random", "skyjo_step_random_profile", "skyjo_step_host", "skyjo_set_host_threads", "skyjo_observe", "skyjo_stats_device",
-    "skyjo_stats_host", "skyjo_stats_clear", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
+    "skyjo_step", "skyjo_step_random", "skyjo_rollout_random", "skyjo_profile_begin", "skyjo_profile_end",
+    "skyjo_step_random_profile", "skyjo_step_host", "skyjo_set_host_threads", "skyjo_observe", "skyjo_stats_device",
+    "skyjo_stats_host", "skyjo_stats_clear", "skyjo_quiesce", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
     "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
     "skyjo_host_policy", "skyjo_host_expand_packed",
 ]
@@ -51,6 +52,10 @@ class SkyjoConfig(C.Structure):
 class SkyjoOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("obs_dev", "action_mask_dev", "agent_dev", "done_dev", "reward_dev", "final_score_dev")]
+
+
+class SkyjoRollout(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs_dev", "action_mask_dev", "agent_dev", "done_dev")]
 
 
 class SkyjoEnvDebug(C.Structure):
@@ -112,6 +117,9 @@ def load():
         "skyjo_seed": (i32, [vp, u64, vp]),
         "skyjo_step": (i32, [vp, vp, i32, vp]),
         "skyjo_step_random": (i32, [vp, i32, vp]),
+        "skyjo_rollout_random": (i32, [vp, i32, C.POINTER(SkyjoRollout), vp]),
+        "skyjo_profile_begin": (i32, [vp]),
+        "skyjo_profile_end": (i32, [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]),
         "skyjo_step_random_profile": (i32, [vp, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                              C.POINTER(i64), C.POINTER(i64)]),
         "skyjo_step_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -120,6 +128,7 @@ def load():
         "skyjo_stats_device": (i32, [vp, vp, vp]),
         "skyjo_stats_host": (i32, [vp, vp, vp]),
         "skyjo_stats_clear": (i32, [vp, vp]),
+        "skyjo_quiesce": (i32, [vp, vp]),
         "skyjo_export_debug": (i32, [vp, i64, i64, vp, vp]),
         "skyjo_check": (i32, [vp, vp]),
         "skyjo_step_count": (i64, [vp]),

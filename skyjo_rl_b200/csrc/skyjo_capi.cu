@@ -29,6 +29,7 @@ namespace skyjo {
 #endif
 #define SKYJO_DECL(n)                                                                                     \
     SKYJO_WEAK cudaError_t launch_step_##n(const StepParams &, bool, bool, cudaStream_t);                 \
+    SKYJO_WEAK cudaError_t launch_rollout_##n(const StepParams &, const RolloutParams &, bool, cudaStream_t); \
     SKYJO_WEAK cudaError_t launch_observe_##n(const StepParams &, bool, int, int8_t *, int8_t *, int, int, cudaStream_t);
 SKYJO_DECL(1) SKYJO_DECL(2) SKYJO_DECL(3) SKYJO_DECL(4) SKYJO_DECL(5) SKYJO_DECL(6)
 SKYJO_DECL(7) SKYJO_DECL(8) SKYJO_DECL(9) SKYJO_DECL(10) SKYJO_DECL(11) SKYJO_DECL(12)
@@ -37,6 +38,9 @@ SKYJO_DECL(7) SKYJO_DECL(8) SKYJO_DECL(9) SKYJO_DECL(10) SKYJO_DECL(11) SKYJO_DE
 static const step_launch_fn kStep[SKYJO_MAX_PLAYERS] = {
     launch_step_1, launch_step_2, launch_step_3, launch_step_4,  launch_step_5,  launch_step_6,
     launch_step_7, launch_step_8, launch_step_9, launch_step_10, launch_step_11, launch_step_12};
+static const rollout_launch_fn kRollout[SKYJO_MAX_PLAYERS] = {
+    launch_rollout_1, launch_rollout_2, launch_rollout_3, launch_rollout_4,  launch_rollout_5,  launch_rollout_6,
+    launch_rollout_7, launch_rollout_8, launch_rollout_9, launch_rollout_10, launch_rollout_11, launch_rollout_12};
 static const observe_launch_fn kObserve[SKYJO_MAX_PLAYERS] = {
     launch_observe_1, launch_observe_2, launch_observe_3, launch_observe_4,  launch_observe_5,  launch_observe_6,
     launch_observe_7, launch_observe_8, launch_observe_9, launch_observe_10, launch_observe_11, launch_observe_12};
@@ -61,6 +65,14 @@ struct SkyjoHandle {
     unsigned long long t;   // lockstep counter
     long long launches;
     int steps_since_deal;
+    // Refill windows (see open_window / close_window): the envs that finish during window w are
+    // flagged in needs_deal array w & 1 and re-dealt by one flagged deal launch when the window
+    // closes; with the in-kernel policy that launch runs on deal_stream, concurrently with window w + 1.
+    uint8_t *flags_base;  // [2][Bpad]
+    int parity;
+    bool deal_async_ready, deal_pending[2], deal_async_enabled;
+    cudaStream_t deal_stream;
+    cudaEvent_t ev_window, ev_deal[2];
     int obs_len;
     int pf_dist;  // L2 prefetch distance of the step kernel, in tiles
     // optional per-kernel event timing (skyjo_step_random_profile)
@@ -133,7 +145,7 @@ static Layout layout_for(int N, long long B) {
     L.next_planes = off; off = align_up(off + np * Bpad * 16, 256);
     L.pile = off;        off = align_up(off + 2 * Bpad * PILE_ROW, 256);
     L.episode = off;     off = align_up(off + Bpad * 4, 256);
-    L.needs_deal = off;  off = align_up(off + Bpad, 256);
+    L.needs_deal = off;  off = align_up(off + 2 * Bpad, 256);
     L.stats = off;       off = align_up(off + (long long)STAT_SLOTS * NUM_STATS * 8, 256);
     L.stats_tmp = off;   off = align_up(off + NUM_STATS * 8, 256);
     L.errflag = off;     off = align_up(off + 4, 256);
@@ -168,7 +180,7 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
         return fail(SKYJO_E_NO_DEVICE, "no CUDA device: libskyjo_b200 has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return fail(SKYJO_E_INVALID, "bad device index");
-    if (!kStep[cfg->num_players - 1] || !kObserve[cfg->num_players - 1])
+    if (!kStep[cfg->num_players - 1] || !kObserve[cfg->num_players - 1] || !kRollout[cfg->num_players - 1])
         return fail(SKYJO_E_INVALID, "this development build does not instantiate that player count");
     const Layout L = layout_for(cfg->num_players, num_envs);
     if (!state_dev || state_bytes < L.total || ((uintptr_t)state_dev & 255)) {
@@ -193,6 +205,11 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     h->st.deck = base + L.pile;
     h->st.episode = (uint32_t *)(base + L.episode);
     h->st.needs_deal = base + L.needs_deal;
+    h->flags_base = base + L.needs_deal;
+    h->parity = 0;
+    h->deal_async_ready = false;
+    h->deal_pending[0] = h->deal_pending[1] = false;
+    h->deal_async_enabled = getenv("SKYJO_SYNC_DEAL") == nullptr;
     h->st.stats = (unsigned long long *)(base + L.stats);
     h->stats_tmp = (long long *)(base + L.stats_tmp);
     h->st.errflag = (uint32_t *)(base + L.errflag);
@@ -245,6 +262,14 @@ static void hostio_release(SkyjoHandle *h) {
 }
 
 int skyjo_destroy(SkyjoHandle *h) {
+    if (h && h->deal_async_ready) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->deal_stream);
+        cudaEventDestroy(h->ev_window);
+        cudaEventDestroy(h->ev_deal[0]);
+        cudaEventDestroy(h->ev_deal[1]);
+        cudaStreamDestroy(h->deal_stream);
+    }
     if (h) hostio_release(h);
     delete h;
     return SKYJO_OK;
@@ -312,12 +337,84 @@ static int launch_deal(SkyjoHandle *h, int flagged, int target_next, const int8_
     return SKYJO_OK;
 }
 
+// ---- refill windows -----------------------------------------------------------------------------
+// A window is a run of consecutive steps (at most deal_period of them) whose finished envs are
+// flagged in needs_deal array `parity`.  Closing it launches the flagged deal D_w that pre-deals
+// the next-but-one episode of those envs and clears their flags.  An episode lasts >= 21 act()
+// calls under legal play, so an env that finished in window w cannot finish again in window w + 1:
+// D_w touches nothing window w + 1 reads (the env's next_planes row, its free deck slot, its flag
+// in the other array) and may run concurrently with it on deal_stream.  It has to be complete
+// before window w + 2 starts, which also is the next user of flag array w & 1.
+static int deal_async_init(SkyjoHandle *h) {
+    if (h->deal_async_ready) return SKYJO_OK;
+    CU(cudaStreamCreateWithFlags(&h->deal_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_window, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_deal[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_deal[1], cudaEventDisableTiming));
+    h->deal_async_ready = true;
+    return SKYJO_OK;
+}
+
+// before the first kernel of a window: the deal that last used this window's flag array is done
+static int open_window(SkyjoHandle *h, cudaStream_t s) {
+    if (h->steps_since_deal == 0 && h->deal_pending[h->parity]) {
+        CU(cudaStreamWaitEvent(s, h->ev_deal[h->parity], 0));
+        h->deal_pending[h->parity] = false;
+    }
+    return SKYJO_OK;
+}
+
+static int close_window(SkyjoHandle *h, cudaStream_t s, bool async) {
+    h->steps_since_deal = 0;
+    if (!h->cfg.auto_reset) return SKYJO_OK;
+    int rc;
+    if (async && h->deal_async_enabled) {
+        rc = deal_async_init(h);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->ev_window, s));
+        CU(cudaStreamWaitEvent(h->deal_stream, h->ev_window, 0));
+        rc = launch_deal(h, 1, 1, nullptr, nullptr, h->deal_stream);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->ev_deal[h->parity], h->deal_stream));
+        h->deal_pending[h->parity] = true;
+    } else {
+        rc = launch_deal(h, 1, 1, nullptr, nullptr, s);
+        if (rc) return rc;
+    }
+    h->parity ^= 1;
+    h->st.needs_deal = h->flags_base + (size_t)h->parity * (size_t)h->Bpad;
+    return SKYJO_OK;
+}
+
+// `s` waits for every deal still running on deal_stream (before anything else touches the state)
+static int join_deals(SkyjoHandle *h, cudaStream_t s) {
+    for (int k = 0; k < 2; ++k)
+        if (h->deal_pending[k]) {
+            CU(cudaStreamWaitEvent(s, h->ev_deal[k], 0));
+            h->deal_pending[k] = false;
+        }
+    return SKYJO_OK;
+}
+
+// close the running window (if any steps are in it) and join: afterwards no flag is set
+static int quiesce(SkyjoHandle *h, cudaStream_t s) {
+    if (h->steps_since_deal > 0) {
+        int rc = close_window(h, s, false);
+        if (rc) return rc;
+    }
+    return join_deals(h, s);
+}
+
 static int reset_common(SkyjoHandle *h, const int8_t *decks, const uint8_t *flips, cudaStream_t s) {
     if (!h) return fail(SKYJO_E_INVALID, "null handle");
     if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
     CU(cudaSetDevice(h->device));
-    CU(cudaMemsetAsync(h->st.needs_deal, 0, (size_t)h->Bpad, s));
-    int rc = launch_deal(h, 0, 0, decks, flips, s);
+    int rc = join_deals(h, s);
+    if (rc) return rc;
+    h->parity = 0;
+    h->st.needs_deal = h->flags_base;
+    CU(cudaMemsetAsync(h->flags_base, 0, 2 * (size_t)h->Bpad, s));
+    rc = launch_deal(h, 0, 0, decks, flips, s);
     if (rc) return rc;
     if (h->cfg.auto_reset) {
         rc = launch_deal(h, 0, 1, nullptr, nullptr, s);
@@ -358,6 +455,8 @@ static int deal_period(const SkyjoHandle *h, bool policy) {
 }
 
 static int step_once(SkyjoHandle *h, const void *actions, int dtype, bool policy, cudaStream_t s) {
+    int rc = open_window(h, s);
+    if (rc) return rc;
     StepParams p = make_params(h);
     p.actions = actions;
     p.action_dtype = dtype;
@@ -367,10 +466,7 @@ static int step_once(SkyjoHandle *h, const void *actions, int dtype, bool policy
     CU(le);
     h->launches += 1;
     h->t += 1;
-    if (h->cfg.auto_reset && ++h->steps_since_deal >= deal_period(h, policy)) {
-        h->steps_since_deal = 0;
-        return launch_deal(h, 1, 1, nullptr, nullptr, s);
-    }
+    if (++h->steps_since_deal >= deal_period(h, policy)) return close_window(h, s, policy);
     return SKYJO_OK;
 }
 
@@ -379,6 +475,10 @@ int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *
     if (action_dtype < SKYJO_ACT_U8 || action_dtype > SKYJO_ACT_I64) return fail(SKYJO_E_INVALID, "bad action dtype");
     if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
     CU(cudaSetDevice(h->device));
+    // external actions may be illegal and end an episode at once: every step is its own window,
+    // refilled in stream order
+    int rc = quiesce(h, (cudaStream_t)stream);
+    if (rc) return rc;
     return step_once(h, actions_dev, action_dtype, false, (cudaStream_t)stream);
 }
 
@@ -386,28 +486,66 @@ int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream) {
     if (!h || n_steps < 0) return fail(SKYJO_E_INVALID, "bad argument");
     if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
     CU(cudaSetDevice(h->device));
-    // a pending external-action cadence must not be stretched: flush it first
-    if (h->cfg.auto_reset && h->steps_since_deal > 0) {
-        h->steps_since_deal = 0;
-        int rc = launch_deal(h, 1, 1, nullptr, nullptr, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
+    cudaStream_t s = (cudaStream_t)stream;
     for (int i = 0; i < n_steps; ++i) {
-        int rc = step_once(h, nullptr, 0, true, (cudaStream_t)stream);
+        int rc = step_once(h, nullptr, 0, true, s);
         if (rc) return rc;
     }
-    if (h->cfg.auto_reset && h->steps_since_deal > 0) {
-        h->steps_since_deal = 0;
-        return launch_deal(h, 1, 1, nullptr, nullptr, (cudaStream_t)stream);
+    // every call ends with its window closed (the deal may still be running on deal_stream)
+    if (h->steps_since_deal > 0) return close_window(h, s, true);
+    return SKYJO_OK;
+}
+
+// Multi-step launches with the in-kernel policy (rollout_kernel, skyjo_step.cuh): n_steps env-steps
+// in ceil(n_steps / K) launches, K = the refill cadence, each followed by one flagged deal launch.
+int skyjo_rollout_random(SkyjoHandle *h, int n_steps, const SkyjoRollout *out, void *stream) {
+    if (!h || n_steps < 0 || !out) return fail(SKYJO_E_INVALID, "bad argument");
+    if (!out->obs_dev || !out->action_mask_dev || !out->agent_dev || !out->done_dev)
+        return fail(SKYJO_E_INVALID, "all four rollout buffers are required");
+    if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long B = h->B, D = h->obs_len;
+    const int K = h->cfg.auto_reset ? deal_period(h, true) : 8;
+    if (h->steps_since_deal > 0) {  // an open window of single steps: close it first
+        int rc = close_window(h, s, true);
+        if (rc) return rc;
+    }
+    const bool aligned = (((uintptr_t)out->obs_dev | (uintptr_t)out->action_mask_dev) & 15) == 0 &&
+                         (B * D) % 16 == 0 && (B * 26) % 16 == 0;
+    for (int t0 = 0; t0 < n_steps; t0 += K) {
+        int rc = open_window(h, s);
+        if (rc) return rc;
+        StepParams p = make_params(h);
+        RolloutParams r;
+        r.K = n_steps - t0 < K ? n_steps - t0 : K;
+        r.obs = (int8_t *)out->obs_dev + (long long)t0 * B * D;
+        r.mask = (int8_t *)out->action_mask_dev + (long long)t0 * B * 26;
+        r.agent = (int8_t *)out->agent_dev + (long long)t0 * B;
+        r.done = (uint8_t *)out->done_dev + (long long)t0 * B;
+        r.publish = t0 + r.K == n_steps ? 1 : 0;
+        r.bulk_ok = aligned ? 1 : 0;
+        prof_begin(h, 0, s);
+        cudaError_t le = kRollout[h->cfg.num_players - 1](p, r, h->cfg.observe_other_player_indirect != 0, s);
+        prof_end(h, s);
+        CU(le);
+        h->launches += 1;
+        h->t += (unsigned long long)r.K;
+        rc = close_window(h, s, true);
+        if (rc) return rc;
     }
     return SKYJO_OK;
 }
 
-int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double *step_ms, double *deal_ms,
-                              int64_t *n_step_launches, int64_t *n_deal_launches) {
-    if (!h || !step_ms || !deal_ms) return fail(SKYJO_E_INVALID, "null argument");
+int skyjo_profile_begin(SkyjoHandle *h) {
+    if (!h) return fail(SKYJO_E_INVALID, "null handle");
     h->profiling = true;
-    int rc = skyjo_step_random(h, n_steps, stream);
+    return SKYJO_OK;
+}
+
+int skyjo_profile_end(SkyjoHandle *h, void *stream, double *step_ms, double *deal_ms, int64_t *n_step_launches,
+                      int64_t *n_deal_launches) {
+    if (!h || !step_ms || !deal_ms) return fail(SKYJO_E_INVALID, "null argument");
     h->profiling = false;
     cudaError_t se = cudaStreamSynchronize((cudaStream_t)stream);
     double sum[2] = {0.0, 0.0};
@@ -423,13 +561,21 @@ int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double 
     }
     h->prof_events.clear();
     h->prof_kind.clear();
-    if (rc) return rc;
     CU(se);
     *step_ms = sum[0];
     *deal_ms = sum[1];
     if (n_step_launches) *n_step_launches = cnt[0];
     if (n_deal_launches) *n_deal_launches = cnt[1];
     return SKYJO_OK;
+}
+
+int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double *step_ms, double *deal_ms,
+                              int64_t *n_step_launches, int64_t *n_deal_launches) {
+    if (!h || !step_ms || !deal_ms) return fail(SKYJO_E_INVALID, "null argument");
+    h->profiling = true;
+    const int rc = skyjo_step_random(h, n_steps, stream);
+    const int rc2 = skyjo_profile_end(h, stream, step_ms, deal_ms, n_step_launches, n_deal_launches);
+    return rc ? rc : rc2;
 }
 
 static int default_host_threads() {
@@ -490,6 +636,8 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     uint8_t *act_dev = (uint8_t *)h->outs.agent_dev;
     CU(cudaMemcpyAsync(act_dev, actions_host, B, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(h->counter_dev, 0, 4, s));
+    rc = quiesce(h, s);
+    if (rc) return rc;
     // step kernel only; the refill deal is queued after the pack kernel so that it overlaps the copies
     StepParams p = make_params(h);
     p.actions = act_dev;
@@ -506,11 +654,10 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(h->ev_packed_ready, s));
-    if (h->cfg.auto_reset) {  // external actions may end any episode at once: refill after every step
-        h->steps_since_deal = 0;
-        rc = launch_deal(h, 1, 1, nullptr, nullptr, s);
-        if (rc) return rc;
-    }
+    // external actions may end any episode at once: refill after every step (queued behind the pack
+    // kernel so that it overlaps the copies)
+    rc = close_window(h, s, false);
+    if (rc) return rc;
     CU(cudaStreamWaitEvent(cs, h->ev_packed_ready, 0));
     if (want_small) {
         CU(cudaMemcpyAsync(h->packed_host, h->packed_dev, B * 4, cudaMemcpyDeviceToHost, cs));
@@ -603,10 +750,20 @@ int skyjo_stats_clear(SkyjoHandle *h, void *stream) {
     return SKYJO_OK;
 }
 
+int skyjo_quiesce(SkyjoHandle *h, void *stream) {
+    if (!h) return fail(SKYJO_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    return quiesce(h, (cudaStream_t)stream);
+}
+
 int skyjo_export_debug(SkyjoHandle *h, int64_t env0, int64_t count, SkyjoEnvDebug *out_dev, void *stream) {
     if (!h || !out_dev) return fail(SKYJO_E_INVALID, "null argument");
     if (env0 < 0 || count <= 0 || env0 + count > h->B) return fail(SKYJO_E_INVALID, "env range out of bounds");
     CU(cudaSetDevice(h->device));
+    {
+        int rc = join_deals(h, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     const unsigned grid = (unsigned)((count + 127) / 128);
     export_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->st, h->Bpad, h->cfg.num_players,
                                                           h->cfg.observe_other_player_indirect ? 1 : 0, env0, count,
@@ -619,6 +776,10 @@ int skyjo_export_debug(SkyjoHandle *h, int64_t env0, int64_t count, SkyjoEnvDebu
 int skyjo_check(SkyjoHandle *h, void *stream) {
     if (!h) return fail(SKYJO_E_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
+    {
+        int rc = join_deals(h, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     uint32_t flag = 0;
     CU(cudaMemcpyAsync(&flag, h->st.errflag, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
@@ -636,7 +797,10 @@ int64_t skyjo_step_count(const SkyjoHandle *h) { return h ? (int64_t)h->t : -1; 
 int skyjo_set_step_count(SkyjoHandle *h, int64_t t) {
     if (!h || t < 0) return fail(SKYJO_E_INVALID, "bad argument");
     h->t = (unsigned long long)t;
-    h->steps_since_deal = h->cfg.auto_reset ? 1 : 0;  // force a refill after the next step
+    // the restored buffer was saved quiesced (no flag set): start a fresh window on flag array 0
+    h->steps_since_deal = 0;
+    h->parity = 0;
+    h->st.needs_deal = h->flags_base;
     return SKYJO_OK;
 }
 int64_t skyjo_launch_count(const SkyjoHandle *h) { return h ? h->launches : -1; }

@@ -180,9 +180,10 @@ SKYJO_HD void store_env(U128 *planes, long long Bpad, long long e, const Env<N> 
 }
 
 // One env-step for env e: SkyjoGame.act + rewards + (on episode end) auto-reset install.
-// `s` holds the loaded state and is updated in place; the caller stores it back.
+// `s` holds the loaded state and is updated in place; the caller stores it back.  With POLICY
+// the action is the uniform legal choice selected by `policy_rnd` = policy_random(seed, env, t).
 template <int N, bool IND, bool POLICY>
-SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int action) {
+SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int action, uint32_t policy_rnd = 0u) {
     Outcome oc;
     oc.done_code = SKYJO_RUNNING;
     oc.act_class = -1;
@@ -213,7 +214,7 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
     uint32_t hidden = row_hidden(a), flags = row_flags(a);
     const uint32_t legal = legal_bits(hidden, flags, place_phase);
     const unsigned long long genv = p.first_env + (unsigned long long)e;
-    if (POLICY) action = policy_pick(p.seed, genv, p.t, legal);
+    if (POLICY) action = policy_select(policy_rnd, legal);
     const bool is_legal = action >= 0 && action < 26 && ((legal >> action) & 1u);
     uint32_t step = (uint32_t)(hdr & HDR_STEP_MASK);
     const uint8_t *deck = p.st.deck + (((hdr & HDR_SLOT) ? p.Bpad : 0ll) + e) * PILE_ROW;
@@ -396,11 +397,15 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
     if (oc.done_code != SKYJO_RUNNING) {
         bool installed = false;
         if (p.auto_reset) {
-            const U128 Q0 = ld128(p.st.next_planes + e);
+            // all 1 + N planes of the pre-dealt episode are requested at once (one memory round
+            // trip, L2 hits when the previous step prefetched them); the episode tag is checked
+            // on the loaded header
+            Env<N> nx;
+            load_env<N>(p.st.next_planes, p.Bpad, e, nx);
             const uint32_t want = ((uint32_t)(hdr >> HDR_EPLO_SH) + 1u) & 15u;
-            if ((Q0.y & 15u) == want) {
+            if (((uint32_t)(nx.hdr >> HDR_EPLO_SH) & 15u) == want) {
                 const uint32_t old_slot = (hdr & HDR_SLOT) ? 1u : 0u;
-                load_env<N>(p.st.next_planes, p.Bpad, e, s);
+                s = nx;
                 oc.pf_new = PF_KEEP;
                 hdr = s.hdr | HDR_DIRTY;
                 hist = s.hist;
@@ -439,7 +444,7 @@ SKYJO_HD uint32_t spread4(uint32_t x) {  // 4 nibbles (16 bits) -> 4 bytes
 
 // collect_observation (skyjo.py:148-199) of `observer` on state s.
 template <int N, bool IND>
-SKYJO_HD void encode_words(const Env<N> &s, int observer, ObsWords<N, IND> &o) {
+SKYJO_HD void encode_words(const Env<N> &s, int observer, ObsWords<N, IND> &o, uint32_t *observer_hidden = nullptr) {
     uint32_t min_sum24 = 255u, min_hid = 12u;
 #pragma unroll
     for (int q = 0; q < N; ++q) {
@@ -486,6 +491,7 @@ SKYJO_HD void encode_words(const Env<N> &s, int observer, ObsWords<N, IND> &o) {
         o.s[4 + 3 * N] = tail;
     }
     // action mask, 26 bytes of 0/1
+    if (observer_hidden) *observer_hidden = row_hidden(ob);
     const uint32_t lb = legal_bits(row_hidden(ob), row_flags(ob), (s.hdr & HDR_PHASE) != 0);
 #pragma unroll
     for (int k = 0; k < 7; ++k) o.m[k] = bits01(lb >> (4 * k));

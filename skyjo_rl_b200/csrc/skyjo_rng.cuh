@@ -94,15 +94,21 @@ SKYJO_HD int nth_set_bit(uint32_t m, int k) {
     return (int)pos;
 }
 
-// random_admissible_policy.py:26-28: uniform over the legal actions
-SKYJO_HD int policy_pick(uint64_t seed, uint64_t env, uint64_t t, uint32_t legal_bits) {
-    U4 r = rng_block(seed, env, PURPOSE_POLICY, (uint32_t)t, (uint32_t)(t >> 32));
+// random_admissible_policy.py:26-28: uniform over the legal actions.  The random word depends
+// only on (seed, env, t), so a kernel can draw it before the state has arrived.
+SKYJO_HD uint32_t policy_random(uint64_t seed, uint64_t env, uint64_t t) {
+    return rng_block(seed, env, PURPOSE_POLICY, (uint32_t)t, (uint32_t)(t >> 32)).x;
+}
+SKYJO_HD int policy_select(uint32_t rnd, uint32_t legal_bits) {
 #if defined(__CUDA_ARCH__)
     int cnt = __popc(legal_bits);
 #else
     int cnt = __builtin_popcount(legal_bits);
 #endif
-    return nth_set_bit(legal_bits, (int)bounded(r.x, (uint32_t)cnt));
+    return nth_set_bit(legal_bits, (int)bounded(rnd, (uint32_t)cnt));
+}
+SKYJO_HD int policy_pick(uint64_t seed, uint64_t env, uint64_t t, uint32_t legal_bits) {
+    return policy_select(policy_random(seed, env, t), legal_bits);
 }
 
 }  // namespace skyjo

@@ -256,6 +256,18 @@ struct StepParams {
     int pf_dist;  // step kernel: L2 prefetch distance in tiles (0 = off)
 };
 
+// Time-major outputs of the multi-step rollout kernel: slice k of each tensor receives what a
+// single fused step would have published after env-step k of the launch.
+struct RolloutParams {
+    int8_t *obs;     // [K][B][D]
+    int8_t *mask;    // [K][B][26]
+    int8_t *agent;   // [K][B]
+    uint8_t *done;   // [K][B]
+    int K;           // env-steps in this launch
+    int publish;     // 1: the last step also writes the bound [B, ...] outputs of the handle
+    int bulk_ok;     // every slice 16-byte aligned -> TMA bulk stores
+};
+
 enum : uint32_t { ERR_NEXT_NOT_READY = 1, ERR_BAD_DECK = 2, ERR_BAD_FLIPS = 4 };
 
 }  // namespace skyjo

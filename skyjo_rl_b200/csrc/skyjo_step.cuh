@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
                              : "memory");
         }
     }
+    // the policy's random word depends only on (seed, env, t): drawn before the wait, so CTAs that
+    // were scheduled early have work to do while the previous step's grid drains
+    uint32_t policy_rnd = 0u;
+    if (POLICY) policy_rnd = policy_random(p.seed, p.first_env + (unsigned long long)e, p.t);
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
     Env<N> s;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     uint32_t dirty_rows = 0, pf_new = PF_KEEP;
     int done_code = SKYJO_RUNNING;
     if (valid) {
-        const Outcome oc = env_step<N, IND, POLICY>(p, e, s, action);
+        const Outcome oc = env_step<N, IND, POLICY>(p, e, s, action, policy_rnd);
         dirty_rows = oc.dirty_rows;
         pf_new = oc.pf_new;
         done_code = oc.done_code;
@@ -197,9 +201,17 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     // ---- observation + mask of the next agent -------------------------------------------
     {
         OW ow;
-        encode_words<N, IND>(s, (int)(s.hdr >> HDR_CUR_SH) & 0xF, ow);
+        uint32_t next_hidden;
+        encode_words<N, IND>(s, (int)(s.hdr >> HDR_CUR_SH) & 0xF, ow, &next_hidden);
         stage_stream<OW::NW, 3>(ow.s, s_obs, tid);
         stage_stream<7, 2>(ow.m, s_mask, tid);
+        // The next agent is about to draw with no hidden card left: the next step ends this game
+        // (skyjo.py:350-356) and installs the pre-dealt episode.  Pull its planes into L2 now.
+        if (valid && p.auto_reset && next_hidden == 0u && !(s.hdr & (HDR_PHASE | HDR_TERMINATED))) {
+#pragma unroll
+            for (int q = 0; q <= N; ++q)
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.st.next_planes + (long long)q * p.Bpad + e));
+        }
     }
     // state write-back after the staging: a draw-pile prefetch issued by env_step has had the
     // whole encode to arrive before the header is stored
@@ -229,6 +241,142 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
     }
+}
+
+// ---- multi-step rollout with the in-kernel policy ------------------------------------------------
+// K consecutive env-steps of the same 32 games per warp in ONE launch (the loop of
+// sample_game.py:10-21 unrolled in time): the state is loaded once, stays in registers across the
+// K steps and is written back once; every step still encodes the next agent's observation and
+// action mask and stores them -- into slice k of time-major rollout tensors [K][B][...] -- exactly
+// as K single-step launches would have published them one after the other.  With an in-kernel
+// policy nothing outside the kernel consumes step k's outputs before step k+1, so the K - 1 state
+// round trips through HBM, the launch ramps / tails and the exposed load latency between steps
+// are pure overhead; this kernel removes them.  Rewards keep the [B, N] "last finished episode,
+// cleared by the next step" semantics of the single-step kernel (skyjo_env.py:242-252).
+template <int N, bool IND>
+__global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N))
+    rollout_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RolloutParams r) {
+    using OW = ObsWords<N, IND>;
+    constexpr int D = OW::D;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *s_obs = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + TILE * D);
+    __shared__ int s_stats[WARPS][NUM_STATS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile0 = (long long)blockIdx.x * TILE;
+    const long long e = tile0 + tid;
+    const bool valid = e < p.B;
+    const unsigned long long genv = p.first_env + (unsigned long long)e;
+    s_stats[warp][lane] = 0;
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    if (p.pf_dist > 0 && lane == 0) {
+        const long long pt = (long long)blockIdx.x + p.pf_dist;
+        if (pt < (long long)gridDim.x) {
+            const U128 *src = p.st.planes + pt * TILE;
+#pragma unroll
+            for (int q = 0; q <= N; ++q)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src + (long long)q * p.Bpad),
+                             "r"((uint32_t)(TILE * 16))
+                             : "memory");
+        }
+    }
+    uint32_t policy_rnd = policy_random(p.seed, genv, p.t);
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+
+    Env<N> s;
+    load_env_dev<N>(p.st.planes, p.Bpad, e, s);
+    __syncwarp();
+
+    const long long w0 = tile0 + 32 * warp;
+    const long long left = p.B - w0;
+    const uint32_t rows_valid = left >= 32 ? 32u : (left > 0 ? (uint32_t)left : 0u);
+    uint32_t dirty_all = 0;
+    long long lane_stat = 0;  // lane k accumulates statistics entry k over the K steps
+    for (int k = 0; k < r.K; ++k) {
+        if (k > 0) {
+            policy_rnd = policy_random(p.seed, genv, p.t + (unsigned long long)k);
+            // the staging tile is reused: the previous step's bulk stores must have read it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            __syncwarp();
+        }
+        int act_class = -1, done_code = SKYJO_RUNNING;
+        uint32_t pf_new = PF_KEEP;
+        if (valid) {
+            const Outcome oc = env_step<N, IND, true>(p, e, s, 0, policy_rnd);
+            dirty_all |= oc.dirty_rows;
+            pf_new = oc.pf_new;
+            done_code = oc.done_code;
+            act_class = oc.act_class;
+            if (oc.done_code != SKYJO_RUNNING || oc.reshuffled) {  // rare events
+                int *st = s_stats[warp];
+                if (oc.scored) {
+                    atomicAdd(&st[SKYJO_STAT_EPISODES], 1);
+                    atomicAdd(&st[SKYJO_STAT_EPISODE_STEPS], oc.ep_steps);
+                    atomicAdd(&st[SKYJO_STAT_SCORE_RAW_SUM], oc.raw_sum);
+                    atomicAdd(&st[SKYJO_STAT_WINNER_RAW_SUM], oc.winner_raw);
+                    atomicAdd(&st[SKYJO_STAT_FINISHER_RAW_SUM], oc.fin_raw);
+                    if (oc.penalised) {
+                        atomicAdd(&st[SKYJO_STAT_PENALISED], 1);
+                        atomicAdd(&st[SKYJO_STAT_PENALISED_RAW_SUM], oc.fin_raw);
+                    }
+                    atomicAdd(&st[SKYJO_STAT_REFUNDS], oc.refunds);
+                    if (oc.starter0) atomicAdd(&st[SKYJO_STAT_STARTER_SEAT0], 1);
+                    atomicAdd(&st[SKYJO_STAT_WINS_SEAT0 + oc.winner], 1);
+                }
+                if (oc.reshuffled) atomicAdd(&st[SKYJO_STAT_RESHUFFLES], 1);
+                if (oc.done_code == SKYJO_DONE_ILLEGAL) atomicAdd(&st[SKYJO_STAT_ILLEGAL], 1);
+                if (oc.done_code == SKYJO_DONE_TRUNCATED) atomicAdd(&st[SKYJO_STAT_TRUNCATED], 1);
+            }
+        }
+        const bool last = k + 1 == r.K;
+        {
+            OW ow;
+            uint32_t next_hidden;
+            encode_words<N, IND>(s, (int)(s.hdr >> HDR_CUR_SH) & 0xF, ow, &next_hidden);
+            stage_stream<OW::NW, 3>(ow.s, s_obs, tid);
+            stage_stream<7, 2>(ow.m, s_mask, tid);
+            if (valid && p.auto_reset && next_hidden == 0u && !(s.hdr & (HDR_PHASE | HDR_TERMINATED))) {
+#pragma unroll
+                for (int q = 0; q <= N; ++q)
+                    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.st.next_planes + (long long)q * p.Bpad + e));
+            }
+        }
+        // the byte below the drawn card (requested by env_step) becomes the prefetched pile top
+        if (pf_new != PF_KEEP) s.hdr = hdr_pf_set(s.hdr, pf_new);
+        if (valid) {
+            const int8_t ag = (int8_t)((s.hdr >> HDR_CUR_SH) & 0xF);
+            r.agent[(long long)k * p.B + e] = ag;
+            r.done[(long long)k * p.B + e] = (uint8_t)done_code;
+            if (last && r.publish) {
+                p.agent[e] = ag;
+                p.done[e] = (uint8_t)done_code;
+            }
+        }
+        const unsigned cls = __reduce_add_sync(0xFFFFFFFFu, act_class >= 0 ? 1u << (8 * act_class) : 0u);
+        if (lane >= SKYJO_STAT_ACT_DRAW_PILE && lane <= SKYJO_STAT_ACT_FLIP)
+            lane_stat += (cls >> (8 * (lane - SKYJO_STAT_ACT_DRAW_PILE))) & 0xFFu;
+        if (lane == SKYJO_STAT_STEPS)
+            lane_stat += (cls & 0xFFu) + ((cls >> 8) & 0xFFu) + ((cls >> 16) & 0xFFu) + (cls >> 24);
+        fence_async_smem();
+        __syncwarp();
+        store_warp_slice(smem + (size_t)warp * 32 * D, r.obs + ((long long)k * p.B + w0) * D, D, rows_valid,
+                         r.bulk_ok != 0, lane);
+        store_warp_slice(smem + (size_t)TILE * D + (size_t)warp * 32 * 26, r.mask + ((long long)k * p.B + w0) * 26, 26u,
+                         rows_valid, r.bulk_ok != 0, lane);
+        if (last && r.publish) {
+            store_warp_slice(smem + (size_t)warp * 32 * D, p.obs + w0 * D, D, rows_valid, p.bulk_ok != 0, lane);
+            store_warp_slice(smem + (size_t)TILE * D + (size_t)warp * 32 * 26, p.mask + w0 * 26, 26u, rows_valid,
+                             p.bulk_ok != 0, lane);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    }
+    if (valid) store_env_dev<N>(p.st.planes, p.Bpad, e, s, dirty_all, PF_KEEP);
+    {
+        const long long v = lane_stat + s_stats[warp][lane];
+        if (v) atomicAdd(&p.st.stats[((blockIdx.x * WARPS + warp) % STAT_SLOTS) * NUM_STATS + lane], (unsigned long long)v);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
 
 // Stand-alone observe (SimpleSkyjoEnv.observe, skyjo_env.py:199-214): encodes the view of
@@ -275,6 +423,7 @@ __global__ void __launch_bounds__(TILE) observe_kernel(const StepParams p, int a
 
 // launchers implemented per player count in skyjo_step_inst.cu
 typedef cudaError_t (*step_launch_fn)(const StepParams &, bool indirect, bool policy, cudaStream_t);
+typedef cudaError_t (*rollout_launch_fn)(const StepParams &, const RolloutParams &, bool indirect, cudaStream_t);
 typedef cudaError_t (*observe_launch_fn)(const StepParams &, bool indirect, int agent, int8_t *, int8_t *, int, int,
                                          cudaStream_t);
 

@@ -35,6 +35,23 @@ cudaError_t SKYJO_CAT(launch_step_, SKYJO_N)(const StepParams &p, bool indirect,
     return cudaLaunchKernelEx(&cfg, step_kernel<N, false, false>, p);
 }
 
+cudaError_t SKYJO_CAT(launch_rollout_, SKYJO_N)(const StepParams &p, const RolloutParams &r, bool indirect,
+                                                 cudaStream_t s) {
+    constexpr int N = SKYJO_N;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.Bpad / TILE));
+    cfg.blockDim = dim3(TILE);
+    cfg.dynamicSmemBytes = (size_t)TILE * ((indirect ? 31 : 19 + 12 * N) + 26);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (indirect) return cudaLaunchKernelEx(&cfg, rollout_kernel<N, true>, p, r);
+    return cudaLaunchKernelEx(&cfg, rollout_kernel<N, false>, p, r);
+}
+
 cudaError_t SKYJO_CAT(launch_observe_, SKYJO_N)(const StepParams &p, bool indirect, int agent, int8_t *obs,
                                                  int8_t *mask, int reset_outputs, int bulk_ok, cudaStream_t s) {
     constexpr int N = SKYJO_N;

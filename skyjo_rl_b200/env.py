@@ -184,6 +184,38 @@ class BatchedSkyjoEnv:
         assert self._has_reset, "reset() needs to be called before step"
         _lib.check(self._L.skyjo_step_random(self._h, int(n_steps), self._stream()))
 
+    def rollout_random(self, n_steps, out=None):
+        """The env-steps of step_random(n_steps) as multi-step launches (state in registers across
+        up to 8 steps per kernel); what each step publishes goes to slice t of time-major tensors
+        {"observations": int8[T,B,D], "action_mask": int8[T,B,26], "agent_selection": int8[T,B],
+        "done_code": uint8[T,B]} (allocated here unless `out` is given)."""
+        assert self._has_reset, "reset() needs to be called before step"
+        T, B = int(n_steps), self.num_envs
+        if out is None:
+            with torch.cuda.device(self.device):
+                out = {"observations": torch.empty((T, B, self.obs_len), dtype=torch.int8, device=self.device),
+                       "action_mask": torch.empty((T, B, 26), dtype=torch.int8, device=self.device),
+                       "agent_selection": torch.empty((T, B), dtype=torch.int8, device=self.device),
+                       "done_code": torch.empty((T, B), dtype=torch.uint8, device=self.device)}
+        for k, shape in (("observations", (B, self.obs_len)), ("action_mask", (B, 26)), ("agent_selection", (B,)),
+                         ("done_code", (B,))):
+            t = out[k]
+            assert t.is_contiguous() and t.device == self.device and t.shape[0] >= T and tuple(t.shape[1:]) == shape
+        ro = _lib.SkyjoRollout(out["observations"].data_ptr(), out["action_mask"].data_ptr(),
+                               out["agent_selection"].data_ptr(), out["done_code"].data_ptr())
+        _lib.check(self._L.skyjo_rollout_random(self._h, T, C.byref(ro), self._stream()))
+        return out
+
+    def profile_begin(self):
+        _lib.check(self._L.skyjo_profile_begin(self._h))
+
+    def profile_end(self):
+        sm, dm = C.c_double(0), C.c_double(0)
+        ns, nd = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.skyjo_profile_end(self._h, self._stream(), C.byref(sm), C.byref(dm), C.byref(ns),
+                                             C.byref(nd)))
+        return {"step_ms": sm.value, "deal_ms": dm.value, "step_launches": ns.value, "deal_launches": nd.value}
+
     def step_random_profile(self, n_steps):
         """step_random with per-kernel CUDA-event timing; returns a dict of device times."""
         sm, dm = C.c_double(0), C.c_double(0)
@@ -298,6 +330,7 @@ class BatchedSkyjoEnv:
     # ---- checkpoint ---------------------------------------------------------------------
     def state_dict(self):
         """Everything needed to resume: the flat device state plus the published outputs."""
+        _lib.check(self._L.skyjo_quiesce(self._h, self._stream()))
         return {
             "config": {k: getattr(self._cfg, k) for k, _ in _lib.SkyjoConfig._fields_},
             "num_envs": self.num_envs, "seed": self._seed, "first_global_env_id": self.first_global_env_id,
@@ -310,6 +343,7 @@ class BatchedSkyjoEnv:
 
     def load_state_dict(self, sd):
         assert sd["num_envs"] == self.num_envs and sd["config"]["num_players"] == self.num_players
+        _lib.check(self._L.skyjo_quiesce(self._h, self._stream()))
         for name in ("observations", "action_mask", "agent_selection", "done_code", "rewards", "final_scores"):
             getattr(self, name).copy_(sd[name])
         self._state.copy_(sd["state"])

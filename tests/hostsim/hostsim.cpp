@@ -164,7 +164,8 @@ static void step_all(HostSim *h, const int32_t *actions) {
         Env<N> s;
         load_env<N>(h->st.planes, h->Bpad, e, s);
         const int action = POLICY ? 0 : load_action(actions, SKYJO_ACT_I32, e);
-        const Outcome oc = env_step<N, IND, POLICY>(p, e, s, action);
+        const Outcome oc = env_step<N, IND, POLICY>(p, e, s, action,
+                                                    POLICY ? policy_random(p.seed, p.first_env + (unsigned long long)e, p.t) : 0u);
         store_env<N>(h->st.planes, h->Bpad, e, s, oc.dirty_rows, oc.pf_new);
         h->agent[e] = (int8_t)((s.hdr >> HDR_CUR_SH) & 0xF);
         h->done[e] = (uint8_t)oc.done_code;

@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=512)
 ap.add_argument("--preroll", type=int, default=640)
 ap.add_argument("--indirect", action="store_true")
 ap.add_argument("--tag", default="")
+ap.add_argument("--rollout", type=int, default=0, help="time rollout_random with this many steps per call")
 a = ap.parse_args()
 env = BatchedSkyjoEnv(num_envs=a.envs, num_players=a.players, observe_other_player_indirect=a.indirect, seed=0)
 env.reset()
@@ -33,6 +34,26 @@ torch.cuda.synchronize()
 wall = ev0.elapsed_time(ev1) * 1e3 / a.steps
 prof = env.step_random_profile(a.steps)
 env.check()
+if a.rollout:
+    T = a.rollout
+    ro = env.rollout_random(T)
+    torch.cuda.synchronize()
+    ev0.record()
+    reps = max(1, a.steps // T)
+    for _ in range(reps):
+        env.rollout_random(T, ro)
+    ev1.record()
+    torch.cuda.synchronize()
+    us = ev0.elapsed_time(ev1) * 1e3 / (reps * T)
+    env.profile_begin()
+    for _ in range(reps):
+        env.rollout_random(T, ro)
+    pr = env.profile_end()
+    env.check()
+    print(json.dumps({"tag": a.tag + " rollout", "N": a.players, "B": a.envs, "T": T, "us_per_step_all": round(us, 2),
+                      "rollout_kernel_us_per_step": round(1e3 * pr["step_ms"] / (reps * T), 2),
+                      "deal_kernel_us": round(1e3 * pr["deal_ms"] / max(pr["deal_launches"], 1), 2),
+                      "steps_per_s": round(a.envs / (us * 1e-6), 0)}))
 print(json.dumps({"tag": a.tag, "N": a.players, "B": a.envs, "indirect": a.indirect,
                   "us_per_step_all": round(wall, 2),
                   "step_kernel_us": round(1e3 * prof["step_ms"] / prof["step_launches"], 2),
