@@ -283,6 +283,42 @@ def run_ours(args, rank, local_rank, world):
     stats = env.stats(all_reduce=world > 1)
     env.check()
 
+    # the same env-steps as multi-step launches (rollout_kernel: state in registers across 8 steps, every
+    # step's obs / mask / agent / done stored into slice t of time-major rollout tensors)
+    rollout = None
+    if args.rollout_steps > 0:
+        D = env.obs_len
+        T = min(args.rollout_steps, int(8e9 // (B * (D + 28))) // 8 * 8)
+        if T >= 8:
+            ro = env.rollout_random(T)
+            reps = max(1, min(K, 1024) // T)
+            for _ in range(2):
+                env.rollout_random(T, ro)
+            barrier()
+            ev0.record()
+            for _ in range(reps):
+                env.rollout_random(T, ro)
+                if world > 1:
+                    dist.all_reduce(env.stats_tensor())
+            ev1.record()
+            barrier()
+            rms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(rms, op=dist.ReduceOp.MAX)
+            rms = float(rms.item()) / (reps * T)
+            env.profile_begin()
+            for _ in range(reps):
+                env.rollout_random(T, ro)
+            rp = env.profile_end()
+            env.check()
+            rollout = {"value": B * world / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms,
+                       "kernel": "skyjo::rollout_kernel", "env_steps_per_launch": 8, "rollout_len": T,
+                       "kernel_us_per_env_step": 1e3 * rp["step_ms"] / (reps * T),
+                       "hbm_bytes_written_per_env_step": D + 28,
+                       "note": "state stays in registers for 8 consecutive env-steps per launch; every step's obs, "
+                               "mask, agent and done are stored into slice t of [T,B,...] rollout tensors"}
+            del ro
+
     # end to end through the host-buffer C-ABI entry
     e2e = None
     if args.e2e_steps > 0:
@@ -306,7 +342,7 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout,
             "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")},
         }
         print(json.dumps(line), flush=True)
@@ -381,6 +417,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--preroll", type=int, default=640)
     ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--rollout-steps", type=int, default=64, help="rollout length T of the multi-step path (0 = skip)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="CPU-seconds of oracle work (baseline sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--python-reference", action="store_true")

@@ -82,7 +82,7 @@ struct SkyjoHandle {
     // skyjo_step_host wire staging (skyjo_hostio.cuh), created on first use
     bool hostio_ready;
     cudaStream_t copy_stream;
-    cudaEvent_t ev_packed_ready, ev_small_done, ev_all_done;
+    cudaEvent_t ev_chunk_ready[HOSTIO_MAX_CHUNKS], ev_small_done[HOSTIO_MAX_CHUNKS], ev_counter_done, ev_all_done;
     uint32_t *packed_dev, *packed_host;     // [B]
     unsigned int *counter_dev, *counter_host;
     double *entries_host, *entries_dev;     // host-mapped pinned, [cap][1 + N]
@@ -254,8 +254,11 @@ static void hostio_release(SkyjoHandle *h) {
     cudaFreeHost(h->packed_host);
     cudaFreeHost(h->counter_host);
     cudaFreeHost(h->entries_host);
-    cudaEventDestroy(h->ev_packed_ready);
-    cudaEventDestroy(h->ev_small_done);
+    for (int c = 0; c < HOSTIO_MAX_CHUNKS; ++c) {
+        cudaEventDestroy(h->ev_chunk_ready[c]);
+        cudaEventDestroy(h->ev_small_done[c]);
+    }
+    cudaEventDestroy(h->ev_counter_done);
     cudaEventDestroy(h->ev_all_done);
     cudaStreamDestroy(h->copy_stream);
     h->hostio_ready = false;
@@ -368,7 +371,7 @@ static int close_window(SkyjoHandle *h, cudaStream_t s, bool async) {
     h->steps_since_deal = 0;
     if (!h->cfg.auto_reset) return SKYJO_OK;
     int rc;
-    if (async && h->deal_async_enabled) {
+    if (async && h->deal_async_enabled && !h->profiling) {  // per-kernel event timing measures each kernel alone
         rc = deal_async_init(h);
         if (rc) return rc;
         CU(cudaEventRecord(h->ev_window, s));
@@ -601,8 +604,11 @@ static int hostio_init(SkyjoHandle *h) {
     const size_t B = (size_t)h->B, N = (size_t)h->cfg.num_players;
     h->sparse_cap = (unsigned int)(B / 8 > 64 ? B / 8 : 64);
     CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&h->ev_packed_ready, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_small_done, cudaEventDisableTiming));
+    for (int c = 0; c < HOSTIO_MAX_CHUNKS; ++c) {
+        CU(cudaEventCreateWithFlags(&h->ev_chunk_ready[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_small_done[c], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&h->ev_counter_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_all_done, cudaEventDisableTiming));
     CU(cudaMalloc(&h->packed_dev, B * 4));
     CU(cudaMalloc(&h->counter_dev, 4));
@@ -634,42 +640,66 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     };
     // the agent buffer doubles as the staging area of the uint8 actions: it is rewritten by the step
     uint8_t *act_dev = (uint8_t *)h->outs.agent_dev;
-    CU(cudaMemcpyAsync(act_dev, actions_host, B, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(h->counter_dev, 0, 4, s));
     rc = quiesce(h, s);
     if (rc) return rc;
-    // step kernel only; the refill deal is queued after the pack kernel so that it overlaps the copies
+    const bool want_small = mask_host || agent_host || done_host || reward_host;
+    if (want_small) CU(cudaMemsetAsync(h->counter_dev, 0, 4, s));
+    // env ranges: multiples of ENV_PAD envs, so every range starts on a tile and on a 16-byte boundary
+    int chunks = h->B >= (1 << 18) ? 4 : (h->B >= (1 << 16) ? 2 : 1);
+    if (const char *g = getenv("SKYJO_HOST_CHUNKS")) chunks = atoi(g);
+    if (chunks < 1) chunks = 1;
+    if (chunks > HOSTIO_MAX_CHUNKS) chunks = HOSTIO_MAX_CHUNKS;
+    const long long per = align_up((h->B + chunks - 1) / chunks, ENV_PAD);
+    long long c_begin[HOSTIO_MAX_CHUNKS], c_end[HOSTIO_MAX_CHUNKS];
+    int nc = 0;
+    for (long long b = 0; b < h->B; b += per) {
+        c_begin[nc] = b;
+        c_end[nc] = b + per < h->B ? b + per : h->B;
+        ++nc;
+    }
     StepParams p = make_params(h);
     p.actions = act_dev;
     p.action_dtype = SKYJO_ACT_U8;
-    CU(kStep[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, false, s));
-    h->launches += 1;
-    h->t += 1;
-    const bool want_small = mask_host || agent_host || done_host || reward_host;
-    if (want_small) {
-        pack_host_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(
-            h->st.planes, h->Bpad, h->B, (int)N, (const uint8_t *)h->outs.done_dev, (const double *)h->outs.reward_dev,
-            h->packed_dev, h->counter_dev, reward_host ? h->entries_dev : nullptr, h->sparse_cap);
+    for (int c = 0; c < nc; ++c) {
+        const size_t e0 = (size_t)c_begin[c], n = (size_t)(c_end[c] - c_begin[c]);
+        CU(cudaMemcpyAsync(act_dev + e0, actions_host + e0, n, cudaMemcpyHostToDevice, s));
+        p.tile_off = c_begin[c] / TILE;
+        p.tiles = (long long)((n + TILE - 1) / TILE);
+        CU(kStep[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, false, s));
         h->launches += 1;
-        CU(cudaGetLastError());
+        if (want_small) {
+            pack_host_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+                h->st.planes, h->Bpad, c_begin[c], c_end[c], (int)N, (const uint8_t *)h->outs.done_dev,
+                (const double *)h->outs.reward_dev, h->packed_dev, h->counter_dev,
+                reward_host ? h->entries_dev : nullptr, h->sparse_cap);
+            h->launches += 1;
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(h->ev_chunk_ready[c], s));
+        CU(cudaStreamWaitEvent(cs, h->ev_chunk_ready[c], 0));
+        if (want_small) {
+            CU(cudaMemcpyAsync(h->packed_host + e0, h->packed_dev + e0, n * 4, cudaMemcpyDeviceToHost, cs));
+            CU(cudaEventRecord(h->ev_small_done[c], cs));
+        }
+        if (obs_host)
+            CU(cudaMemcpyAsync(obs_host + e0 * (size_t)h->obs_len, (const int8_t *)h->outs.obs_dev + e0 * (size_t)h->obs_len,
+                               n * (size_t)h->obs_len, cudaMemcpyDeviceToHost, cs));
     }
-    CU(cudaEventRecord(h->ev_packed_ready, s));
-    // external actions may end any episode at once: refill after every step (queued behind the pack
-    // kernel so that it overlaps the copies)
+    h->t += 1;
+    if (reward_host) {
+        CU(cudaMemcpyAsync(h->counter_host, h->counter_dev, 4, cudaMemcpyDeviceToHost, cs));
+        CU(cudaEventRecord(h->ev_counter_done, cs));
+    }
+    CU(cudaEventRecord(h->ev_all_done, cs));
+    // external actions may end any episode at once: refill after every step (queued behind the last
+    // pack kernel, it overlaps the copies)
+    h->steps_since_deal = 1;
     rc = close_window(h, s, false);
     if (rc) return rc;
-    CU(cudaStreamWaitEvent(cs, h->ev_packed_ready, 0));
-    if (want_small) {
-        CU(cudaMemcpyAsync(h->packed_host, h->packed_dev, B * 4, cudaMemcpyDeviceToHost, cs));
-        CU(cudaMemcpyAsync(h->counter_host, h->counter_dev, 4, cudaMemcpyDeviceToHost, cs));
-        CU(cudaEventRecord(h->ev_small_done, cs));
-    }
-    if (obs_host) CU(cudaMemcpyAsync(obs_host, h->outs.obs_dev, B * (size_t)h->obs_len, cudaMemcpyDeviceToHost, cs));
-    CU(cudaEventRecord(h->ev_all_done, cs));
     lap(0);
 
     if (want_small) {
-        // previous call's reward rows back to zero while the packed words travel
+        // previous call's reward rows back to zero while the first packed words travel
         if (reward_host) {
             if (h->last_reward_host != reward_host) {
                 memset(reward_host, 0, B * N * 8);
@@ -679,19 +709,22 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
             }
             h->last_reward_rows.clear();
         }
-        CU(cudaEventSynchronize(h->ev_small_done));
-        lap(1);
         const uint32_t *packed = h->packed_host;
-        const long long nB = h->B;
-        h->pool->run([=](int part, int parts) {
-            const long long e0 = nB * part / parts, e1 = nB * (part + 1) / parts;
-            expand_packed(packed, e0, e1, mask_host, agent_host, done_host);
-        });
-        lap(2);
+        for (int c = 0; c < nc; ++c) {
+            CU(cudaEventSynchronize(h->ev_small_done[c]));
+            lap(1);
+            const long long b0 = c_begin[c], nB = c_end[c] - c_begin[c];
+            h->pool->run([=](int part, int parts) {
+                const long long e0 = b0 + nB * part / parts, e1 = b0 + nB * (part + 1) / parts;
+                expand_packed(packed, e0, e1, mask_host, agent_host, done_host);
+            });
+            lap(2);
+        }
         if (reward_host) {
+            CU(cudaEventSynchronize(h->ev_counter_done));
             const unsigned int cnt = *h->counter_host;
             if (cnt <= h->sparse_cap) {
-                // the pack kernel finished before ev_small_done: its writes to the mapped buffer are visible
+                // every pack kernel finished before ev_counter_done: its writes to the mapped buffer are visible
                 for (unsigned int i = 0; i < cnt; ++i) {
                     const double *src = h->entries_host + (size_t)i * (1 + N);
                     const long long e = (long long)reinterpret_cast<const unsigned long long *>(src)[0];

@@ -13,6 +13,8 @@
 //     by the previous call are re-zeroed first.  If more envs finish than the buffer holds
 //     (mass illegal actions) the call falls back to copying the dense reward tensor.
 //   * observations (D bytes per env) are copied as they are.
+// The batch is processed in up to HOSTIO_MAX_CHUNKS env ranges (step kernel, pack kernel and copies
+// per range), so that the link is already busy with range c while the GPU steps range c + 1.
 // N = 4, direct observations: 67 + 4 = 71 B per env-step instead of 127 B.
 #pragma once
 #include <cuda_runtime.h>
@@ -30,17 +32,19 @@
 namespace skyjo {
 
 constexpr int PACK_DONE_SH = 26, PACK_AGENT_SH = 28;
+constexpr int HOSTIO_MAX_CHUNKS = 8;
 
 // One thread per env: the packed word from the state planes (the same legal_bits the fused step
 // kernel encoded the mask row from) and the compaction of finished envs' reward rows.
 // `entries` is host-mapped pinned memory: entry i = (1 + N) doubles, the first holding the env
 // index as uint64.
-__global__ void __launch_bounds__(256) pack_host_kernel(const U128 *planes, long long Bpad, long long B, int N,
+__global__ void __launch_bounds__(256) pack_host_kernel(const U128 *planes, long long Bpad, long long e_begin,
+                                                        long long B, int N,
                                                         const uint8_t *done, const double *reward,
                                                         uint32_t *packed, unsigned int *counter,
                                                         double *entries, unsigned int cap) {
-    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (e >= B) return;
+    const long long e = e_begin + (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= B) return;  // B = end of this launch's env range
     const U128 P0 = ld128(planes + e);
     const uint64_t hdr = pack64(P0.x, P0.y);
     const uint32_t cur = (uint32_t)(hdr >> HDR_CUR_SH) & 0xFu;

@@ -254,6 +254,9 @@ struct StepParams {
     int bulk_ok;  // obs / mask base pointers 16-byte aligned -> TMA bulk stores
     int pdl;      // host side: launch with programmatic stream serialization
     int pf_dist;  // step kernel: L2 prefetch distance in tiles (0 = off)
+    // step kernel over a sub-range of the batch (skyjo_step_host pipelines chunks against the
+    // copies): first tile and number of tiles of this launch; tiles == 0 means the whole batch
+    long long tile_off, tiles;
 };
 
 // Time-major outputs of the multi-step rollout kernel: slice k of each tensor receives what a

@@ -26,7 +26,10 @@ namespace skyjo {
 #ifndef SKYJO_STEP_WARPS_SMALL
 #define SKYJO_STEP_WARPS_SMALL 32
 #endif
-#define STEP_WARPS_PER_SM(N) ((N) <= 5 ? SKYJO_STEP_WARPS_SMALL : ((N) <= 8 ? 20 : 12))
+#ifndef SKYJO_STEP_WARPS_MID
+#define SKYJO_STEP_WARPS_MID 20
+#endif
+#define STEP_WARPS_PER_SM(N) ((N) <= 5 ? SKYJO_STEP_WARPS_SMALL : ((N) <= 8 ? SKYJO_STEP_WARPS_MID : 12))
 #define STEP_MIN_CTAS(N) ((STEP_WARPS_PER_SM(N) * 32) / TILE)
 
 constexpr int WARPS = TILE / 32;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     __shared__ int s_stats[WARPS][NUM_STATS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long tile0 = (long long)blockIdx.x * TILE;
+    const long long tile0 = ((long long)blockIdx.x + p.tile_off) * TILE;
     const long long e = tile0 + tid;
     const bool valid = e < p.B;
     // Warps never wait for each other: each owns its 32 rows of the tile, its stat counters and
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     if (p.pf_dist > 0 && lane == 0) {
         const long long pt = (long long)blockIdx.x + p.pf_dist;
         if (pt < (long long)gridDim.x) {
-            const U128 *src = p.st.planes + pt * TILE;
+            const U128 *src = p.st.planes + (pt + p.tile_off) * TILE;
 #pragma unroll
             for (int q = 0; q <= N; ++q)
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src + (long long)q * p.Bpad),

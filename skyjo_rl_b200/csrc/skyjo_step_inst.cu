@@ -14,7 +14,7 @@ namespace skyjo {
 
 cudaError_t SKYJO_CAT(launch_step_, SKYJO_N)(const StepParams &p, bool indirect, bool policy, cudaStream_t s) {
     constexpr int N = SKYJO_N;
-    const dim3 grid((unsigned)(p.Bpad / TILE)), block(TILE);
+    const dim3 grid((unsigned)(p.tiles > 0 ? p.tiles : p.Bpad / TILE)), block(TILE);
     const size_t smem = (size_t)TILE * ((indirect ? 31 : 19 + 12 * N) + 26);
     // programmatic stream serialization: the grid may be scheduled while its predecessor drains
     cudaLaunchConfig_t cfg = {};

@@ -1,2 +1,3 @@
-for d in 0 1184 2368 4736 9472; do python tools/variants.py run --env SKYJO_PF_DIST=$d base; done
-for v in keep stream keepstream w24 w28; do python tools/variants.py run --env SKYJO_PF_DIST=0 $v; python tools/variants.py run --env SKYJO_PF_DIST=4736 $v; done
+(cd build/old_tree && python tools/quick_bench.py --players 8 --envs 16777216 --steps 64 --tag old16M; python tools/quick_bench.py --players 8 --envs 4194304 --steps 128 --tag old4M; python tools/quick_bench.py --players 8 --envs 4194304 --steps 512 --tag old4M-512)
+python tools/quick_bench.py --players 8 --envs 4194304 --steps 512 --tag new4M-512
+SKYJO_PF_DIST=0 python tools/quick_bench.py --players 8 --envs 4194304 --steps 512 --tag new4M-512-pf0
