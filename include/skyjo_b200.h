@@ -216,6 +216,16 @@ int skyjo_stats_device(SkyjoHandle *h, int64_t *out_dev, void *stream);
 int skyjo_stats_host(SkyjoHandle *h, int64_t *out_host, void *stream);
 int skyjo_stats_clear(SkyjoHandle *h, void *stream);
 
+/* Policy side of a rollout (BASELINE config 4): masked softmax + categorical sample of one action
+ * per env in one launch -- what RLlib's TorchCategorical does on TorchActionMaskModel's output
+ * (action_mask_model.py:63-71).  logits float32[B,26]; mask int8[B,26] (null = the bound
+ * action_mask output); illegal actions have probability exactly 0; the draw is an inverse-CDF
+ * sample from one Philox uniform keyed by (sample_seed, global env id, lockstep counter).
+ * Writes actions uint8[B] (feed them to skyjo_step), logp float32[B] of the drawn action and,
+ * if not null, the entropy float32[B] of the masked distribution. */
+int skyjo_sample_actions(SkyjoHandle *h, const float *logits_dev, const int8_t *mask_dev,
+                         uint64_t sample_seed, uint8_t *actions_dev, float *logp_dev,
+                         float *entropy_dev, void *stream);
 /* Closes the running refill window and makes `stream` wait for the library's internal streams:
  * work queued on `stream` afterwards may read or overwrite the state buffer (checkpointing). */
 int skyjo_quiesce(SkyjoHandle *h, void *stream);

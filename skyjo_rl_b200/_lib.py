@@ -31,7 +31,7 @@ EXPORTS = [
     "skyjo_destroy", "skyjo_bind_outputs", "skyjo_reset", "skyjo_reset_injected", "skyjo_seed",
     "skyjo_step", "skyjo_step_random", "skyjo_rollout_random", "skyjo_profile_begin", "skyjo_profile_end",
     "skyjo_step_random_profile", "skyjo_step_host", "skyjo_set_host_threads", "skyjo_observe", "skyjo_stats_device",
-    "skyjo_stats_host", "skyjo_stats_clear", "skyjo_quiesce", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
+    "skyjo_stats_host", "skyjo_stats_clear", "skyjo_sample_actions", "skyjo_quiesce", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
     "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
     "skyjo_host_policy", "skyjo_host_expand_packed",
 ]
@@ -128,6 +128,7 @@ def load():
         "skyjo_stats_device": (i32, [vp, vp, vp]),
         "skyjo_stats_host": (i32, [vp, vp, vp]),
         "skyjo_stats_clear": (i32, [vp, vp]),
+        "skyjo_sample_actions": (i32, [vp, vp, vp, u64, vp, vp, vp, vp]),
         "skyjo_quiesce": (i32, [vp, vp]),
         "skyjo_export_debug": (i32, [vp, i64, i64, vp, vp]),
         "skyjo_check": (i32, [vp, vp]),

@@ -16,6 +16,7 @@
 #include "skyjo_deal.cuh"
 #include "skyjo_hostio.cuh"
 #include "skyjo_rng.cuh"
+#include "skyjo_sample.cuh"
 #include "skyjo_state.cuh"
 #include "skyjo_step.cuh"
 
@@ -780,6 +781,21 @@ int skyjo_stats_clear(SkyjoHandle *h, void *stream) {
     if (!h) return fail(SKYJO_E_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
     CU(cudaMemsetAsync(h->st.stats, 0, (size_t)STAT_SLOTS * NUM_STATS * 8, (cudaStream_t)stream));
+    return SKYJO_OK;
+}
+
+int skyjo_sample_actions(SkyjoHandle *h, const float *logits_dev, const int8_t *mask_dev, uint64_t sample_seed,
+                         uint8_t *actions_dev, float *logp_dev, float *entropy_dev, void *stream) {
+    if (!h || !logits_dev || !actions_dev || !logp_dev) return fail(SKYJO_E_INVALID, "null argument");
+    if (!mask_dev && !h->bound) return fail(SKYJO_E_NOT_BOUND, "no mask given and no outputs bound");
+    if (((uintptr_t)logits_dev & 7) || ((uintptr_t)(mask_dev ? mask_dev : (const int8_t *)h->outs.action_mask_dev) & 1))
+        return fail(SKYJO_E_INVALID, "logits must be 8-byte aligned, the mask 2-byte aligned");
+    CU(cudaSetDevice(h->device));
+    const int8_t *mask = mask_dev ? mask_dev : (const int8_t *)h->outs.action_mask_dev;
+    sample_actions_kernel<<<(unsigned)((h->B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        logits_dev, mask, h->B, h->first_env, sample_seed, h->t, actions_dev, logp_dev, entropy_dev);
+    h->launches += 1;
+    CU(cudaGetLastError());
     return SKYJO_OK;
 }
 

@@ -236,6 +236,40 @@ class BatchedSkyjoEnv:
         _lib.check(self._L.skyjo_step_host(self._h, ptr(actions), ptr(obs), ptr(mask), ptr(agent), ptr(done),
                                            ptr(reward), self._stream()))
 
+    def sample_actions(self, logits, mask=None, seed=0, actions=None, logp=None, entropy=None):
+        """Fused masked softmax + categorical sample (csrc/skyjo_sample.cuh): float32 logits [B,26]
+        -> uint8 actions [B] for step(), float32 logp [B] (and entropy [B] if a tensor is given).
+        `mask` defaults to the live action_mask buffer (zero copy)."""
+        B = self.num_envs
+        assert logits.dtype == torch.float32 and logits.is_contiguous() and tuple(logits.shape) == (B, 26)
+        mask = self.action_mask if mask is None else mask
+        assert mask.dtype == torch.int8 and mask.is_contiguous() and tuple(mask.shape) == (B, 26)
+        if actions is None:
+            actions = torch.empty(B, dtype=torch.uint8, device=self.device)
+        if logp is None:
+            logp = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.check(self._L.skyjo_sample_actions(self._h, logits.data_ptr(), mask.data_ptr(), int(seed),
+                                                actions.data_ptr(), logp.data_ptr(),
+                                                entropy.data_ptr() if entropy is not None else None, self._stream()))
+        return actions, logp
+
+    def bind_outputs(self, observations=None, action_mask=None, agent_selection=None, done_code=None, rewards=None,
+                     final_scores=None):
+        """Redirect the kernels' outputs (e.g. to slice t of a rollout storage: the env then writes
+        the learner's tensors in place).  Omitted tensors keep their current buffer."""
+        B, N, D = self.num_envs, self.num_players, self.obs_len
+        spec = {"observations": (observations, torch.int8, (B, D)), "action_mask": (action_mask, torch.int8, (B, 26)),
+                "agent_selection": (agent_selection, torch.int8, (B,)), "done_code": (done_code, torch.uint8, (B,)),
+                "rewards": (rewards, torch.float64, (B, N)), "final_scores": (final_scores, torch.float64, (B, N))}
+        for name, (t, dt, shape) in spec.items():
+            if t is not None:
+                assert t.dtype == dt and tuple(t.shape) == shape and t.is_contiguous() and t.device == self.device, name
+                setattr(self, name, t)
+        outs = _lib.SkyjoOutputs(self.observations.data_ptr(), self.action_mask.data_ptr(),
+                                 self.agent_selection.data_ptr(), self.done_code.data_ptr(),
+                                 self.rewards.data_ptr(), self.final_scores.data_ptr())
+        _lib.check(self._L.skyjo_bind_outputs(self._h, C.byref(outs)))
+
     def set_host_threads(self, n=0):
         """Worker threads step_host uses to expand the packed mask / agent / done words (0 = default)."""
         _lib.check(self._L.skyjo_set_host_threads(self._h, int(n)))
