@@ -27,7 +27,7 @@ namespace skyjo {
 #define SKYJO_STEP_WARPS_SMALL 32
 #endif
 #ifndef SKYJO_STEP_WARPS_MID
-#define SKYJO_STEP_WARPS_MID 20
+#define SKYJO_STEP_WARPS_MID 28
 #endif
 #define STEP_WARPS_PER_SM(N) ((N) <= 5 ? SKYJO_STEP_WARPS_SMALL : ((N) <= 8 ? SKYJO_STEP_WARPS_MID : 12))
 #define STEP_MIN_CTAS(N) ((STEP_WARPS_PER_SM(N) * 32) / TILE)
