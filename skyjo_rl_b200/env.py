@@ -354,7 +354,10 @@ class BatchedSkyjoEnv:
         return [GameView(arr[i], self.num_players) for i in range(count)]
 
     def game_view(self, env_index):
-        return self.export(env_index, 1)[0]
+        v = self.export(env_index, 1)[0]
+        if v.is_terminated:  # frozen env (auto_reset=False): the scores of the finished game
+            v.game_metrics["final_score"] = [float(x) for x in self.final_scores[env_index].tolist()]
+        return v
 
     def render(self, env_index=0, mode="human"):
         """SimpleSkyjoEnv.render (skyjo_env.py:269-274) for one env of the batch."""
@@ -418,12 +421,15 @@ class GameView:
         return [v - 2 for v in range(15) for _ in range(int(self.discard_hist[v]))]
 
     def render_table(self):
-        """Board in the format of SkyjoGame.render_table (skyjo.py:508-564)."""
+        """Board in the format of SkyjoGame.render_table (skyjo.py:507-564)."""
         hand = self.hand_card if -2 <= self.hand_card <= 12 else "empty"
         top = self.discard_top if self.discard_top != -3 else "empty"
         s = f"{'='*7} render board: {'='*5} \n{'='*7} stats {'='*12} \n"
         s += f"next turn: {self.expected_action[1]} by Player {self.expected_action[0]} \n"
         s += f"holding card player {self.expected_action[0]}: {hand} \ndiscard pile top: {top} \n"
+        if self.is_terminated:  # skyjo.py:516-521
+            res = dict(zip(range(self.num_players), self.game_metrics.get("final_score", [])))
+            s += f"{'='*7} GAME DONE {'='*8} \nResults: {res} \n"
         for p in range(self.num_players):
             arr = self.players_cards[p].astype(np.str_)
             hid = self.players_masked[p] == 2
@@ -433,3 +439,26 @@ class GameView:
             s += f"{'='*7} Player {p} {'='*10} \n"
             s += np.array2string(arr, separator="\t ", formatter={"str_kind": lambda x: str(x)}) + "\n"
         return s
+
+
+def render_action_explainer(action_int):
+    """Text for an action id, format of SkyjoGame.render_action_explainer (skyjo.py:566-590; the
+    row is printed as place_id % 4 there, kept)."""
+    assert action_int in range(0, 26), "action not valid action int {action_int}"
+    if action_int == 24:
+        return "draw from drawpile"
+    if action_int == 25:
+        return "draw from discard pile"
+    if action_int < 12:
+        place_id, head = action_int, f"place card ({action_int}) - "
+    else:
+        place_id, head = action_int - 12, f"handcard discard & reveal card ({action_int}) - "
+    return head + f"col:{place_id // 3} row:{place_id % 4}"
+
+
+def render_actions():
+    """Legend of the 26 action ids, format of SkyjoGame.render_actions (skyjo.py:592-602)."""
+    grid = [[f"{3 * c + r}/{12 + 3 * c + r}" for c in range(4)] for r in range(3)]
+    body = "\n ".join("[" + "\t ".join(row) + "]" for row in grid)
+    return ("action ids 0-25: \n(put handcard here / reveal this card) \n [" + body + "] \n"
+            "24: draw from drawpile \n 25: draw from discard pile")

@@ -189,3 +189,26 @@ def test_ppo_self_play_learns_to_lower_scores():
     assert sum(h["illegal"] for h in hist) == 0
     assert first > 45 and last < 0.75 * first, (first, last)
     env.check()
+
+
+def test_render_table_matches_reference_strings():
+    """SkyjoGame.render_table (skyjo.py:507-564) of a replayed injected game, incl. the GAME DONE block."""
+    import json
+    import os
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_n3.json")))
+    env = BatchedSkyjoEnv(num_envs=1, num_players=gold["num_players"], auto_reset=False)
+    env.reset_injected(np.array([gold["deck"]], np.int8), np.array([gold["flips"]], np.uint8))
+    for t, a in enumerate(gold["actions"]):
+        if str(t) in gold["renders"]:
+            assert env.game_view(0).render_table() == gold["renders"][str(t)], t
+        env.step(torch.tensor([a], dtype=torch.uint8))
+    assert int(env.done_code[0]) == 1
+    assert env.game_view(0).render_table() == gold["renders"]["final"]
+
+
+def test_sample_run_driver_plays_the_requested_games():
+    from skyjo_rl_b200.sample_game import sample_run          # reference sample_game.py:5-28
+    st = sample_run(games=300, config={"num_players": 2}, num_envs=256)
+    assert st["episodes"] >= 300 and st["illegal"] == 0
+    assert 60 < st["episode_steps"] / st["episodes"] < 95     # SURVEY 9.7: ~76 act() calls per 2-player game
