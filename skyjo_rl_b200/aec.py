@@ -170,6 +170,49 @@ class SkyjoAECView:
         pass
 
 
+class RLlibDictEnv:
+    """Multi-agent dict view of one AEC env: the protocol RLlib's `PettingZooEnv` wrapper gives the
+    reference (`rlskyjo/models/train_model_simple_rllib.py:30-33` registers
+    `PettingZooEnv(skyjo_env.env(**config))`).  `reset()` returns {agent on turn: observation};
+    `step({agent: action})` plays that agent's action and returns (obs, reward, done, info) dicts for
+    the agent that moves next -- or, when the game is over, for every seat at once (the wrapper steps
+    the done agents with None itself) with `done["__all__"] = True`.  Restated from ray 1.9.2's
+    wrapper (ray is not installed here: functional, not pinned, parity)."""
+
+    def __init__(self, aec_env):
+        self.env = aec_env
+        self.agents = list(aec_env.possible_agents)
+        self.observation_space = aec_env.observation_space(self.agents[0])
+        self.action_space = aec_env.action_space(self.agents[0])
+
+    def reset(self):
+        self.env.reset()
+        return {self.env.agent_selection: self.env.observe(self.env.agent_selection)}
+
+    def step(self, action_dict):
+        self.env.step(action_dict[self.env.agent_selection])
+        obs_d, rew_d, done_d, info_d = {}, {}, {}, {}
+        while self.env.agents:
+            obs, rew, done, info = self.env.last()
+            a = self.env.agent_selection
+            obs_d[a], rew_d[a], done_d[a], info_d[a] = obs, rew, done, info
+            if self.env.dones[a]:
+                self.env.step(None)
+            else:
+                break
+        done_d["__all__"] = not self.env.agents
+        return obs_d, rew_d, done_d, info_d
+
+    def seed(self, seed=None):
+        self.env.seed(seed)
+
+    def render(self, mode="human"):
+        return self.env.render(mode)
+
+    def close(self):
+        self.env.close()
+
+
 def env(**config):
     """Drop-in for `rlskyjo.environment.skyjo_env.env(**config)` (skyjo_env.py:19-26): one game on
     cuda:0 with the reference's keyword arguments (`num_players`, `score_penalty`,

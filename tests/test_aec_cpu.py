@@ -8,7 +8,7 @@ import pytest
 
 from hostsim.sim import HostSimEnv
 from oracle import oracle as O
-from skyjo_rl_b200.aec import SkyjoAECView
+from skyjo_rl_b200.aec import RLlibDictEnv, SkyjoAECView
 from skyjo_rl_b200.policy import policy_ra
 
 
@@ -74,3 +74,34 @@ def test_aec_illegal_action_terminates():
     assert got == {a: (-1.0 if a == offender else 0.0) for a in aec.possible_agents}
     with pytest.raises(AssertionError):
         SkyjoAECView(be, 0).step(24)             # OrderEnforcingWrapper: reset first
+
+
+def test_rllib_dict_view_protocol():
+    # the multi-agent dict protocol of RLlib's PettingZooEnv wrapper (train_model_simple_rllib.py:30-33)
+    N, seed, env_id, mr, rr = 3, 5, 2, 1.0, 0.001
+    be = _Backend(num_envs=1, num_players=N, observe_other_player_indirect=True, mean_reward=mr,
+                  reward_refunded=rr, seed=seed, auto_reset=False, first_global_env_id=env_id)
+    menv = RLlibDictEnv(SkyjoAECView(be, 0))
+    g = O.OracleGame(N, 2.0, True)
+    g.reset_rng(seed, env_id, 0)
+    rng = np.random.default_rng(0)
+    obs = menv.reset()
+    for _ in range(300 * N):
+        assert len(obs) == 1
+        (agent, o), = obs.items()
+        pid = g.expected_action[0]
+        assert agent == f"player_{pid}"
+        eo, em = g.collect_observation(pid)
+        np.testing.assert_array_equal(o["observations"], eo)
+        np.testing.assert_array_equal(o["action_mask"], em)
+        a = policy_ra(o["observations"], o["action_mask"], rng)
+        over = g.act(pid, a)
+        obs, rew, done, info = menv.step({agent: a})
+        if over:
+            break
+        assert done == {next(iter(obs)): False, "__all__": False}
+        assert list(rew.values()) == [0]
+    assert done["__all__"] and all(done[f"player_{i}"] for i in range(N))
+    exp = g.final_rewards(mr, rr)
+    assert np.array([rew[f"player_{i}"] for i in range(N)]).tobytes() == exp.tobytes()
+    assert set(obs) == {f"player_{i}" for i in range(N)}
