@@ -74,6 +74,11 @@ struct SkyjoHandle {
     bool deal_async_ready, deal_pending[2], deal_async_enabled;
     cudaStream_t deal_stream;
     cudaEvent_t ev_window, ev_deal[2];
+    // env ranges stepped on their own streams by skyjo_step_random (see step_random_ranges)
+    int n_ranges;
+    bool ranges_ready;
+    cudaStream_t range_stream[HOSTIO_MAX_CHUNKS];
+    cudaEvent_t ev_fork, ev_join[HOSTIO_MAX_CHUNKS];
     int obs_len;
     int pf_dist;  // L2 prefetch distance of the step kernel, in tiles
     // optional per-kernel event timing (skyjo_step_random_profile)
@@ -211,6 +216,11 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     h->deal_async_ready = false;
     h->deal_pending[0] = h->deal_pending[1] = false;
     h->deal_async_enabled = getenv("SKYJO_SYNC_DEAL") == nullptr;
+    h->ranges_ready = false;
+    h->n_ranges = num_envs >= (1 << 18) ? 4 : 1;
+    if (const char *g = getenv("SKYJO_RANGES")) h->n_ranges = atoi(g);  // experiment knob
+    if (h->n_ranges < 1) h->n_ranges = 1;
+    if (h->n_ranges > HOSTIO_MAX_CHUNKS) h->n_ranges = HOSTIO_MAX_CHUNKS;
     h->st.stats = (unsigned long long *)(base + L.stats);
     h->stats_tmp = (long long *)(base + L.stats_tmp);
     h->st.errflag = (uint32_t *)(base + L.errflag);
@@ -266,6 +276,15 @@ static void hostio_release(SkyjoHandle *h) {
 }
 
 int skyjo_destroy(SkyjoHandle *h) {
+    if (h && h->ranges_ready) {
+        cudaSetDevice(h->device);
+        for (int r = 0; r < HOSTIO_MAX_CHUNKS; ++r) {
+            cudaStreamSynchronize(h->range_stream[r]);
+            cudaStreamDestroy(h->range_stream[r]);
+            cudaEventDestroy(h->ev_join[r]);
+        }
+        cudaEventDestroy(h->ev_fork);
+    }
     if (h && h->deal_async_ready) {
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->deal_stream);
@@ -318,10 +337,11 @@ static StepParams make_params(const SkyjoHandle *h) {
 }
 
 static int launch_deal(SkyjoHandle *h, int flagged, int target_next, const int8_t *decks, const uint8_t *flips,
-                       cudaStream_t s) {
+                       cudaStream_t s, long long e_begin = 0, long long e_end = -1) {
     DealParams d;
     d.st = h->st;
-    d.B = h->B;
+    d.B = e_end < 0 ? h->B : e_end;
+    d.e_begin = flagged ? e_begin : 0;
     d.Bpad = h->Bpad;
     d.first_env = h->first_env;
     d.seed = h->seed;
@@ -332,7 +352,7 @@ static int launch_deal(SkyjoHandle *h, int flagged, int target_next, const int8_
     d.decks = decks;
     d.flips = flips;
     const long long per = flagged ? DEAL_SCAN : DEAL_THREADS;
-    const unsigned grid = (unsigned)((h->B + per - 1) / per);
+    const unsigned grid = (unsigned)((d.B - d.e_begin + per - 1) / per);
     prof_begin(h, 1, s);
     deal_kernel<<<grid, DEAL_THREADS, 0, s>>>(d);
     prof_end(h, s);
@@ -486,11 +506,70 @@ int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *
     return step_once(h, actions_dev, action_dtype, false, (cudaStream_t)stream);
 }
 
+// The envs of a batch never interact, so a batch can be stepped as R independent env ranges, each
+// on its own stream: step kernel (tile sub-range) x n, with the range's flagged deal after every
+// window, all in stream order.  The GPU interleaves the ranges, so the launch ramp and tail of one
+// range's kernel are covered by the other ranges' CTAs (at 2^20 envs a lone full-batch launch
+// loses ~7 of 52 us to them), without any cross-kernel memory-ordering assumption.
+static int step_random_ranges(SkyjoHandle *h, int n_steps, cudaStream_t s) {
+    if (!h->ranges_ready) {
+        for (int r = 0; r < HOSTIO_MAX_CHUNKS; ++r) {
+            CU(cudaStreamCreateWithFlags(&h->range_stream[r], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->ev_join[r], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        h->ranges_ready = true;
+    }
+    int rc = quiesce(h, s);  // no window open, no deal pending on deal_stream
+    if (rc) return rc;
+    const int R = h->n_ranges;
+    const long long per = align_up((h->B + R - 1) / R, ENV_PAD);
+    long long b0[HOSTIO_MAX_CHUNKS], b1[HOSTIO_MAX_CHUNKS];
+    int nr = 0;
+    for (long long b = 0; b < h->B; b += per) {
+        b0[nr] = b;
+        b1[nr] = b + per < h->B ? b + per : h->B;
+        ++nr;
+    }
+    CU(cudaEventRecord(h->ev_fork, s));
+    for (int r = 0; r < nr; ++r) CU(cudaStreamWaitEvent(h->range_stream[r], h->ev_fork, 0));
+    const int period = deal_period(h, true);
+    const bool ind = h->cfg.observe_other_player_indirect != 0;
+    int in_window = 0;
+    for (int i = 0; i < n_steps; ++i) {
+        StepParams p = make_params(h);
+        for (int r = 0; r < nr; ++r) {
+            p.tile_off = b0[r] / TILE;
+            p.tiles = (b1[r] - b0[r] + TILE - 1) / TILE;
+            CU(kStep[h->cfg.num_players - 1](p, ind, true, h->range_stream[r]));
+            h->launches += 1;
+        }
+        h->t += 1;
+        if (++in_window >= period || i + 1 == n_steps) {
+            in_window = 0;
+            if (h->cfg.auto_reset) {
+                for (int r = 0; r < nr; ++r) {
+                    rc = launch_deal(h, 1, 1, nullptr, nullptr, h->range_stream[r], b0[r], b1[r]);
+                    if (rc) return rc;
+                }
+                h->parity ^= 1;
+                h->st.needs_deal = h->flags_base + (size_t)h->parity * (size_t)h->Bpad;
+            }
+        }
+    }
+    for (int r = 0; r < nr; ++r) {
+        CU(cudaEventRecord(h->ev_join[r], h->range_stream[r]));
+        CU(cudaStreamWaitEvent(s, h->ev_join[r], 0));
+    }
+    return SKYJO_OK;
+}
+
 int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream) {
     if (!h || n_steps < 0) return fail(SKYJO_E_INVALID, "bad argument");
     if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
+    if (h->n_ranges > 1 && !h->profiling && n_steps >= 2) return step_random_ranges(h, n_steps, s);
     for (int i = 0; i < n_steps; ++i) {
         int rc = step_once(h, nullptr, 0, true, s);
         if (rc) return rc;

@@ -26,6 +26,7 @@ struct DealParams {
     unsigned long long first_env, seed;
     int N;
     int indirect;
+    long long e_begin;  // flagged mode: first env of the scanned range (B is its end)
     int flagged;       // 0: all envs, 1: envs with needs_deal != 0
     int target_next;   // 0: live planes (slot 0), 1: next planes
     const int8_t *decks;   // injected decks int8[B,150] or null
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(DEAL_THREADS) deal_kernel(const DealParams p) 
         if (e < p.B) deal_one(p, e, p.target_next ? 1u : 0u, deck);
         return;
     }
-    const long long base = (long long)blockIdx.x * DEAL_SCAN;
+    const long long base = p.e_begin + (long long)blockIdx.x * DEAL_SCAN;
     if (tid == 0) s_count = 0;
     __syncthreads();
     for (int i = tid; i < DEAL_SCAN; i += DEAL_THREADS) {
