@@ -1,5 +1,7 @@
-for r in 1 2 4 8; do python tools/variants.py run --env SKYJO_RANGES=$r base; done
-python tools/variants.py run --env SKYJO_RANGES=4 --players 8 --envs 4194304 base
-python tools/variants.py run --env SKYJO_RANGES=1 --players 8 --envs 4194304 base
-python tools/variants.py run --env SKYJO_RANGES=4 --players 2 base
-python tools/variants.py run --env SKYJO_RANGES=1 --players 2 base
+T=r1_v5; O=gpurun_out; mkdir -p $O
+export SKYJO_RANGES=1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 730 -c 400 --csv --log-file $O/${T}_launches.csv \
+    python bench.py --steps 400 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 700 -c 2 -f -o $O/${T}_step_full \
+    python bench.py --steps 100 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 > /dev/null 2>&1
+ls -la $O | tail -4
