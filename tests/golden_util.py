@@ -34,3 +34,18 @@ class Golden:
         out = {k: self.z[k][a:b] for k in per_step}
         out.update({k: self.z[k][gi] for k in per_game})
         return out
+
+
+def fingerprint(N):
+    """Per-game statistics of the unmodified reference under policy_ra (make_fingerprint.py)."""
+    import json
+    with open(os.path.join(GOLDEN_DIR, "fingerprint_policy_ra.json")) as f:
+        return json.load(f)["configs"][str(N)]
+
+
+def fingerprint_close(ref, key, value, n, sigmas=5.0):
+    """|value - reference mean| within `sigmas` standard errors of the difference of two sample means
+    (the reference's sd is used for both samples)."""
+    r = ref[key]
+    tol = sigmas * r["sd"] * (1.0 / ref["games"] + 1.0 / n) ** 0.5
+    assert abs(value - r["mean"]) <= tol, f"{key}: {value:.4f} vs reference {r['mean']:.4f} +- {tol:.4f}"
