@@ -75,6 +75,23 @@ enum {
     SKYJO_STAT_WINS_SEAT0 = 17        /* .. +11: first argmin of the final scores */
 };
 
+/* SkyjoConfig.auto_reset.  The reference leaves reset() to the caller (sample_game.py:8-9,
+ * skyjo_env.py:254-267); a batched env has to schedule it per env:
+ *   OFF        the env freezes; every further step returns done (skyjo.py:316-321) until skyjo_reset.
+ *   SAME_STEP  the step that ends an episode also installs the next one: it publishes the ended
+ *              episode's done / rewards / final scores together with the NEW episode's first
+ *              observation, mask and agent.
+ *   NEXT_STEP  phase-locked: the step that ends an episode publishes done / rewards / final scores
+ *              with the TERMINAL observation (agent = the finisher, draw mask, as observe() would
+ *              return after game over); the env's next lockstep slot is the reset: its action is
+ *              ignored, it is not an env-step (not counted in SKYJO_STAT_STEPS), done = 0, rewards
+ *              cleared, and it publishes the new episode's first observation.  An episode is an odd
+ *              number of act() calls, so all envs of the batch stay in the same phase (draw on even,
+ *              place on odd slots) and a warp never executes both transitions.  An episode that
+ *              ends in a place slot (illegal placement, truncation after a placement) is replaced
+ *              at once, which keeps the lock. */
+enum { SKYJO_RESET_OFF = 0, SKYJO_RESET_SAME_STEP = 1, SKYJO_RESET_NEXT_STEP = 2 };
+
 /* Mirrors the keyword arguments of SkyjoGame.__init__ (skyjo.py:20-22) and
  * SimpleSkyjoEnv.__init__ (skyjo_env.py:38-45). */
 typedef struct SkyjoConfig {
@@ -83,7 +100,7 @@ typedef struct SkyjoConfig {
     double score_penalty;
     double mean_reward;
     double reward_refunded;
-    int32_t auto_reset;        /* 1: a finished env starts its next episode in the same step */
+    int32_t auto_reset;        /* SKYJO_RESET_*: what happens to an env whose episode has ended */
     int32_t max_episode_steps; /* 0 = no truncation */
 } SkyjoConfig;
 

@@ -136,7 +136,8 @@ static long long align_up(long long x, long long a) { return (x + a - 1) / a * a
 
 static bool config_ok(const SkyjoConfig *c) {
     return c && c->num_players >= 1 && c->num_players <= SKYJO_MAX_PLAYERS &&  // skyjo.py:24-26
-           c->max_episode_steps >= 0 && c->max_episode_steps <= 0xFFFF;
+           c->max_episode_steps >= 0 && c->max_episode_steps <= 0xFFFF && c->auto_reset >= SKYJO_RESET_OFF &&
+           c->auto_reset <= SKYJO_RESET_NEXT_STEP;
 }
 
 struct Layout {
@@ -178,7 +179,7 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
                  void *state_dev, int64_t state_bytes, SkyjoHandle **out) {
     if (!out) return fail(SKYJO_E_INVALID, "null out pointer");
     *out = nullptr;
-    if (!config_ok(cfg)) return fail(SKYJO_E_INVALID, "invalid config: num_players must be 1..12");
+    if (!config_ok(cfg)) return fail(SKYJO_E_INVALID, "invalid config: num_players must be 1..12, auto_reset one of SKYJO_RESET_*");
     if (num_envs <= 0 || first_global_env_id < 0) return fail(SKYJO_E_INVALID, "num_envs must be > 0");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

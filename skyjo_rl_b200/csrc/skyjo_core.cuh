@@ -195,18 +195,27 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
     const int cur = (int)(hdr >> HDR_CUR_SH) & 0xF;
     const bool place_phase = (hdr & HDR_PHASE) != 0;
 
-    if (hdr & HDR_DIRTY) {
+    // auto_reset == 2 ("next step", phase-locked): an episode that ended in a draw slot is not
+    // replaced in the step that ended it; the env publishes its terminal observation and spends the
+    // NEXT lockstep slot on the reset (action ignored, not an env-step -- the reference's separate
+    // reset() call between two games, sample_game.py:8-9).  An episode lasts an odd number of
+    // act() calls, so every env of the batch is in the same phase at every step and warps never
+    // diverge between the draw and the place transition.
+    const bool reset_slot = (hdr & HDR_TERMINATED) && p.auto_reset == 2;
+    if ((hdr & HDR_DIRTY) || reset_slot) {
         // the previous step ended an episode: its rewards have been consumed
 #pragma unroll
         for (int q = 0; q < N; ++q) p.reward[e * N + q] = 0.0;
         hdr &= ~HDR_DIRTY;
     }
-    if (hdr & HDR_TERMINATED) {
+    if ((hdr & HDR_TERMINATED) && !reset_slot) {
         oc.done_code = SKYJO_DONE_GAME_OVER;  // skyjo.py:316-321: playing a finished game returns True
         s.hdr = hdr;
         return oc;
     }
 
+    do {
+    if (reset_slot) break;
     Row a = s.row[0];
 #pragma unroll
     for (int q = 1; q < N; ++q)
@@ -393,10 +402,15 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
             for (int q = 0; q < N; ++q) p.reward[e * N + q] = 0.0;
         }
     }
-    // ---- episode end: install the pre-dealt next episode, or freeze -----------------------
-    if (oc.done_code != SKYJO_RUNNING) {
+    } while (0);
+    // ---- episode end: install the pre-dealt next episode, defer it to the next slot, or freeze ----
+    if (oc.done_code != SKYJO_RUNNING || reset_slot) {
         bool installed = false;
-        if (p.auto_reset) {
+        // phase-locked mode: an end in a draw slot (game over, illegal draw, truncation after a draw)
+        // is deferred; an end in a place slot (illegal place, truncation after a place) installs at
+        // once -- either way the new episode's first draw falls on a draw slot of the batch
+        const bool defer = p.auto_reset == 2 && !reset_slot && !place_phase;
+        if (p.auto_reset && !defer) {
             // all 1 + N planes of the pre-dealt episode are requested at once (one memory round
             // trip, L2 hits when the previous step prefetched them); the episode tag is checked
             // on the loaded header
@@ -407,7 +421,9 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
                 const uint32_t old_slot = (hdr & HDR_SLOT) ? 1u : 0u;
                 s = nx;
                 oc.pf_new = PF_KEEP;
-                hdr = s.hdr | HDR_DIRTY;
+                // DIRTY: the rewards of the ended episode are cleared by the next step (in a reset
+                // slot they were cleared above, one step after they were published)
+                hdr = reset_slot ? (s.hdr & ~HDR_DIRTY) : (s.hdr | HDR_DIRTY);
                 hist = s.hist;
                 oc.dirty_rows = (1u << N) - 1u;
                 p.st.needs_deal[e] = (uint8_t)(1u | (old_slot << 1));

@@ -45,15 +45,35 @@ SKYJO_HD void deal_one(const DealParams &p, long long e, uint32_t slot, Deck &de
     if (p.decks == nullptr) {
         // skyjo.py:80-81: ten each of -2..12 (codes 0..14), then shuffle
         for (int i = 0; i < 152; ++i) deck.set(i, (uint8_t)(i < 150 ? i / 10 : 0));
-        U4 blk = {0, 0, 0, 0};
-        for (int i = SKYJO_DECK - 1; i >= 1; --i) {
-            const int k = SKYJO_DECK - 1 - i;
-            if ((k & 3) == 0) blk = rng_block(p.seed, genv, PURPOSE_DEAL, ep, (uint32_t)(k >> 2));
-            const uint32_t r = (k & 3) == 0 ? blk.x : (k & 3) == 1 ? blk.y : (k & 3) == 2 ? blk.z : blk.w;
-            const int j = (int)bounded(r, (uint32_t)(i + 1));
-            const uint8_t a = deck.get(i), b = deck.get(j);
-            deck.set(i, b);
-            deck.set(j, a);
+        // Swap k (i = 149 - k) uses word k & 3 of Philox block k >> 2.  The blocks are counter-based,
+        // hence independent of each other and of the swaps: they are generated DEAL_ILP at a time,
+        // one group ahead of the swaps that consume them, so that the ten dependent rounds of a
+        // block overlap those of its neighbours and the shared-memory round trips of the previous
+        // group's swaps (one thread's 38 blocks back to back were 60 % of the kernel's latency).
+        constexpr int DEAL_ILP = 4, NBLK = (SKYJO_DECK - 1 + 3) / 4;
+        U4 cur[DEAL_ILP], nxt[DEAL_ILP];
+#pragma unroll
+        for (int u = 0; u < DEAL_ILP; ++u) cur[u] = rng_block(p.seed, genv, PURPOSE_DEAL, ep, (uint32_t)u);
+#pragma unroll 1
+        for (int g0 = 0; g0 < NBLK; g0 += DEAL_ILP) {
+#pragma unroll
+            for (int u = 0; u < DEAL_ILP; ++u) nxt[u] = rng_block(p.seed, genv, PURPOSE_DEAL, ep, (uint32_t)(g0 + DEAL_ILP + u));
+#pragma unroll
+            for (int u = 0; u < DEAL_ILP; ++u) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int i = SKYJO_DECK - 1 - (4 * (g0 + u) + w);
+                    if (i >= 1) {
+                        const uint32_t r = w == 0 ? cur[u].x : w == 1 ? cur[u].y : w == 2 ? cur[u].z : cur[u].w;
+                        const int j = (int)bounded(r, (uint32_t)(i + 1));
+                        const uint8_t a = deck.get(i), b = deck.get(j);
+                        deck.set(i, b);
+                        deck.set(j, a);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < DEAL_ILP; ++u) cur[u] = nxt[u];
         }
         for (int q = 0; q < N; ++q) {  // skyjo.py:101 choice(12, 2, replace=False)
             U4 r = rng_block(p.seed, genv, PURPOSE_FLIPS, ep, (uint32_t)q);

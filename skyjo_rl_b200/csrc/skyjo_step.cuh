@@ -102,6 +102,14 @@ __device__ __forceinline__ void store_env_dev(U128 *planes, long long Bpad, long
 #endif
 }
 
+// True when the NEXT step of this env will install its pre-dealt episode (so its planes are worth
+// pulling into L2 now).  Same-step reset: the agent on turn is about to draw with no hidden card
+// left, which ends the game (skyjo.py:350-356).  Next-step reset: the episode has just ended.
+__device__ __forceinline__ bool install_next_step(int auto_reset, uint64_t hdr, uint32_t next_hidden) {
+    if (auto_reset == 2) return (hdr & HDR_TERMINATED) != 0;
+    return auto_reset && next_hidden == 0u && !(hdr & (HDR_PHASE | HDR_TERMINATED));
+}
+
 // Stores one warp's 32-row slice of an output tile: one TMA bulk store issued by lane 0 when the
 // slice is complete and 16-byte aligned, a byte loop otherwise (ragged last tile).
 __device__ __forceinline__ void store_warp_slice(const uint8_t *s_src, int8_t *g_dst, uint32_t row_bytes,
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
         stage_stream<7, 2>(ow.m, s_mask, tid);
         // The next agent is about to draw with no hidden card left: the next step ends this game
         // (skyjo.py:350-356) and installs the pre-dealt episode.  Pull its planes into L2 now.
-        if (valid && p.auto_reset && next_hidden == 0u && !(s.hdr & (HDR_PHASE | HDR_TERMINATED))) {
+        if (valid && install_next_step(p.auto_reset, s.hdr, next_hidden)) {
 #pragma unroll
             for (int q = 0; q <= N; ++q)
                 asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.st.next_planes + (long long)q * p.Bpad + e));
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N))
             encode_words<N, IND>(s, (int)(s.hdr >> HDR_CUR_SH) & 0xF, ow, &next_hidden);
             stage_stream<OW::NW, 3>(ow.s, s_obs, tid);
             stage_stream<7, 2>(ow.m, s_mask, tid);
-            if (valid && p.auto_reset && next_hidden == 0u && !(s.hdr & (HDR_PHASE | HDR_TERMINATED))) {
+            if (valid && install_next_step(p.auto_reset, s.hdr, next_hidden)) {
 #pragma unroll
                 for (int q = 0; q <= N; ++q)
                     asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.st.next_planes + (long long)q * p.Bpad + e));

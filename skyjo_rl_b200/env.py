@@ -56,10 +56,17 @@ class BatchedSkyjoEnv:
         self.reward_refunded = float(reward_refunded)
         self.score_penalty = float(score_penalty)
         self.observe_other_player_indirect = bool(observe_other_player_indirect)
-        self.auto_reset = bool(auto_reset)
+        # auto_reset: False (freeze), True / "same_step" (the step that ends an episode installs the next
+        # one), "next_step" (phase-locked: terminal observation first, the reset takes the env's next
+        # lockstep slot -- include/skyjo_b200.h SKYJO_RESET_*)
+        modes = {False: 0, True: 1, "off": 0, "same_step": 1, "next_step": 2, 0: 0, 1: 1, 2: 2}
+        if auto_reset not in modes:
+            raise ValueError(f"auto_reset must be False, True, 'same_step' or 'next_step', not {auto_reset!r}")
+        self.reset_mode = modes[auto_reset]
+        self.auto_reset = self.reset_mode != 0
         self._cfg = _lib.SkyjoConfig(self.num_players, int(self.observe_other_player_indirect),
                                      self.score_penalty, self.mean_reward, self.reward_refunded,
-                                     int(self.auto_reset), int(max_episode_steps))
+                                     self.reset_mode, int(max_episode_steps))
         self.obs_len = self._L.skyjo_obs_len(C.byref(self._cfg))
         self.obs_shape = (self.obs_len,)          # skyjo.py:43-45
         self.action_mask_shape = (_lib.NUM_ACTIONS,)  # skyjo.py:46

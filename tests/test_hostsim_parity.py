@@ -32,6 +32,41 @@ def test_hostsim_rng_rollout_matches_oracle(N, indirect, penalty, mr, rr, B, T):
         assert st["reshuffles"] > 0      # the lazy draw-pile path is exercised
 
 
+@pytest.mark.parametrize("N,indirect,penalty,mr,rr,B,T", [
+    (2, False, 2.0, 1.0, 0.0, 130, 260),
+    (4, False, 2.0, 1.0, 0.01, 140, 420),
+    (3, True, 1.5, 0.0, 0.0, 70, 330),
+    (8, False, 2.0, 1.0, 0.0, 40, 620),
+])
+def test_hostsim_next_step_reset_is_phase_locked_and_matches_oracle(N, indirect, penalty, mr, rr, B, T):
+    # SKYJO_RESET_NEXT_STEP: terminal observation in the ending step, reset in the env's next slot
+    rng_rollout(HostSimEnv, N, indirect, penalty, mr, rr, B, T, reset_mode=2)
+
+
+def test_hostsim_next_step_reset_keeps_the_lock_after_illegal_and_truncated_ends():
+    B, N = 64, 3
+    env = HostSimEnv(num_envs=B, num_players=N, seed=21, auto_reset=2, max_episode_steps=31)
+    env.reset()
+    rng = np.random.default_rng(0)
+    ends = {1: 0, 2: 0, 3: 0}
+    waiting = np.zeros(B, bool)         # envs showing a terminal observation, reset slot ahead
+    for t in range(400):
+        m = env.action_mask
+        live = m[~waiting, 24]
+        assert np.all(live == live[0]), f"phase lock broken at step {t}"
+        draw_slot = live[0] == 1
+        a = np.array([rng.choice(np.flatnonzero(m[i])) for i in range(B)], dtype=np.int32)
+        bad = rng.random(B) < 0.03
+        a[bad] = np.where(m[bad, 24] == 1, 5, 24)   # an action of the other phase: illegal
+        env.step(a)
+        for c in ends:
+            ends[c] += int((env.done_code == c).sum())
+        # an end in a draw slot waits for the next slot; an end in a place slot is replaced at once
+        waiting = (env.done_code != 0) & draw_slot
+    assert ends[2] > 0 and ends[3] > 0
+    assert env.stats()["illegal"] == ends[2] and env.stats()["truncated"] == ends[3]
+
+
 def test_hostsim_illegal_and_truncation():
     B, N = 96, 3
     env = HostSimEnv(num_envs=B, num_players=N, seed=5, auto_reset=True)

@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--launch", type=int, default=0)
     ap.add_argument("--file", default=None, help="attribute inlined code to its frame in this file (basename)")
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--opcodes", action="store_true", help="dynamic opcode mix instead of the per-line table")
     a = ap.parse_args()
     blk = sass_page(a.report, a.kernel, a.launch)
     hdr = blk["hdr"]
@@ -107,6 +108,25 @@ def main():
         tot[1] += tinst
         tot[2] += samp
     print(f"total warp-inst {tot[0]}  thread-inst {tot[1]}  samples {tot[2]}  lanes/inst {tot[1] / max(tot[0], 1):.1f}")
+    if a.opcodes:
+        # dynamic opcode mix (warp-instructions) and how much of it ran at low lane counts
+        ops = collections.defaultdict(lambda: [0, 0])
+        buckets = collections.defaultdict(int)
+        for k in range(n):
+            r = rows[k]
+            inst, tinst = int(r[ci["Instructions Executed"]]), int(r[ci["Thread Instructions Executed"]])
+            m = re.match(r"(?:@!?U?P\w+\s+)?([A-Z0-9_]+)", r[ci["Source"]].strip())
+            op = m.group(1) if m else "?"
+            ops[op][0] += inst
+            ops[op][1] += tinst
+            if inst:
+                lanes = tinst / inst
+                buckets["<4" if lanes < 4 else "<12" if lanes < 12 else "<20" if lanes < 20 else "<28" if lanes < 28 else ">=28"] += inst
+        print("opcode        warp-inst      %  lanes")
+        for op, g in sorted(ops.items(), key=lambda kv: -kv[1][0])[: a.top]:
+            print(f"{op:12s} {g[0]:10d} {100 * g[0] / max(tot[0], 1):6.2f} {g[1] / max(g[0], 1):6.1f}")
+        print("warp-inst by active lanes:", {k: f"{100 * v / max(tot[0], 1):.1f}%" for k, v in sorted(buckets.items())})
+        return
     print(f"{'file:line':32s} {'sass':>5s} {'warp-inst':>11s} {'%':>6s} {'lanes':>6s} {'samples':>8s} {'%':>6s}")
     for key, g in sorted(agg.items(), key=lambda kv: -kv[1][0])[: a.top]:
         print(f"{key[0] + ':' + str(key[1]):32s} {g[3]:5d} {g[0]:11d} {100 * g[0] / max(tot[0], 1):6.2f} "

@@ -21,23 +21,28 @@ ap.add_argument("--preroll", type=int, default=640)
 ap.add_argument("--indirect", action="store_true")
 ap.add_argument("--tag", default="")
 ap.add_argument("--rollout", type=int, default=0, help="time rollout_random with this many steps per call")
+ap.add_argument("--reset", default="same_step", help="same_step | next_step (phase-locked)")
 a = ap.parse_args()
-env = BatchedSkyjoEnv(num_envs=a.envs, num_players=a.players, observe_other_player_indirect=a.indirect, seed=0)
+env = BatchedSkyjoEnv(num_envs=a.envs, num_players=a.players, observe_other_player_indirect=a.indirect, seed=0,
+                      auto_reset=a.reset)
 env.reset()
 env.step_random(a.preroll)
 torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n0 = env.stats()["steps"]
 ev0.record()
 env.step_random(a.steps)
 ev1.record()
 torch.cuda.synchronize()
 wall = ev0.elapsed_time(ev1) * 1e3 / a.steps
+counted = env.stats()["steps"] - n0      # env-steps actually played (reset slots of next_step mode excluded)
 prof = env.step_random_profile(a.steps)
 env.check()
 if a.rollout:
     T = a.rollout
     ro = env.rollout_random(T)
     torch.cuda.synchronize()
+    r0 = env.stats()["steps"]
     ev0.record()
     reps = max(1, a.steps // T)
     for _ in range(reps):
@@ -45,6 +50,7 @@ if a.rollout:
     ev1.record()
     torch.cuda.synchronize()
     us = ev0.elapsed_time(ev1) * 1e3 / (reps * T)
+    rcounted = env.stats()["steps"] - r0
     env.profile_begin()
     for _ in range(reps):
         env.rollout_random(T, ro)
@@ -53,9 +59,10 @@ if a.rollout:
     print(json.dumps({"tag": a.tag + " rollout", "N": a.players, "B": a.envs, "T": T, "us_per_step_all": round(us, 2),
                       "rollout_kernel_us_per_step": round(1e3 * pr["step_ms"] / (reps * T), 2),
                       "deal_kernel_us": round(1e3 * pr["deal_ms"] / max(pr["deal_launches"], 1), 2),
-                      "steps_per_s": round(a.envs / (us * 1e-6), 0)}))
-print(json.dumps({"tag": a.tag, "N": a.players, "B": a.envs, "indirect": a.indirect,
+                      "steps_per_s": round(rcounted / (us * 1e-6 * reps * T), 0)}))
+print(json.dumps({"tag": a.tag, "reset": a.reset, "N": a.players, "B": a.envs, "indirect": a.indirect,
                   "us_per_step_all": round(wall, 2),
                   "step_kernel_us": round(1e3 * prof["step_ms"] / prof["step_launches"], 2),
                   "deal_kernel_us": round(1e3 * prof["deal_ms"] / max(prof["deal_launches"], 1), 2),
-                  "steps_per_s": round(a.envs / (wall * 1e-6), 0)}))
+                  "counted_frac": round(counted / (a.envs * a.steps), 5),
+                  "steps_per_s": round(counted / (wall * 1e-6 * a.steps), 0)}))
