@@ -7,6 +7,10 @@
 One "step" = one launch of the fused kernel = one env-step (SkyjoGame.act + the next agent's
 observation and action mask, i.e. one iteration of reference rlskyjo/game/sample_game.py:10-21)
 for EVERY env of the batch, with the uniform legal policy drawn in-kernel and auto-reset on.
+Auto-reset runs in the phase-locked "next_step" mode by default (include/skyjo_b200.h
+SKYJO_RESET_NEXT_STEP): the lockstep slot an env spends on its reset is NOT an env-step and is not
+counted -- every rate below divides the act() transitions counted by the kernels' statistics
+vector (SKYJO_STAT_STEPS), not launches x envs.  `--reset same_step` gives the other mode.
 Workload = BASELINE.json configs[1]: 4-player SkyJo, 2^20 lockstep envs per GPU, direct
 observations (D = 67).  Envs shard over GPUs by global env id (weak scaling: 2^20 per GPU);
 the only collective is the all-reduce of the 32-entry statistics vector every 64 steps.
@@ -208,7 +212,10 @@ def workload_config(args, world):
     per_step_mb = args.envs * (16 * (1 + N) + 16 + 8 + D + 28) / 1e6
     return {
         "workload": f"{N}-player SkyJo, {args.envs} lockstep envs per GPU, uniform legal policy in-kernel, "
-                    f"fused step+mask+observe, {'indirect' if args.indirect else 'direct'} obs D={D}, auto-reset",
+                    f"fused step+mask+observe, {'indirect' if args.indirect else 'direct'} obs D={D}, "
+                    f"auto-reset ({args.reset})",
+        "reset": args.reset + (" (phase-locked: the slot an env spends on its reset is not an env-step and is not "
+                               "counted; value = counted act() transitions / time)" if args.reset == "next_step" else ""),
         "num_players": N, "envs_per_gpu": args.envs, "global_envs": args.envs * world, "obs_len": D,
         "parallelism": f"env-sharded x{world}, stats all-reduce every 64 steps; per GPU the batch is stepped as 4 "
                        "independent env ranges on 4 CUDA streams",
@@ -221,7 +228,7 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
-    from skyjo_rl_b200 import BatchedSkyjoEnv
+    from skyjo_rl_b200 import BatchedSkyjoEnv, _lib
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
@@ -230,9 +237,16 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     N, B, K, W = args.players, args.envs, args.steps, args.warmup
     env = BatchedSkyjoEnv(num_envs=B, num_players=N, observe_other_player_indirect=args.indirect,
-                          device=dev, seed=args.seed, first_global_env_id=rank * B)
+                          device=dev, seed=args.seed, first_global_env_id=rank * B, auto_reset=args.reset)
     env.reset()
     stats_vec = None
+
+    def counted_steps(allreduce=True):
+        # act() transitions since the last clear_stats(), over all ranks
+        v = env.stats_tensor()
+        if world > 1 and allreduce:
+            dist.all_reduce(v)
+        return int(v[_lib.STAT_NAMES.index("steps")].item())
 
     def run_steps(n):
         nonlocal stats_vec
@@ -268,16 +282,22 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = env.launch_count - l0
-    value = B * world * K / (ms * 1e-3)
+    counted = counted_steps()                 # == B * world * K in same_step mode
+    value = counted / (ms * 1e-3)
+    stats = env.stats(all_reduce=world > 1)   # statistics of the timed region
+    counted_frac = counted / float(B * world * K)
 
     # roofline of the dominant kernel: mean device time of the step kernel from per-launch events
+    env.clear_stats()
     prof = env.step_random_profile(min(K, 512))
     step_us = 1e3 * prof["step_ms"] / max(prof["step_launches"], 1)
-    alg = algorithmic_bytes_per_step(N, args.indirect) * B
+    # algorithmic bytes of one launch = bytes per env-step x env-steps the launch plays (envs in a reset slot
+    # move state but play no step: they are not credited)
+    alg = algorithmic_bytes_per_step(N, args.indirect) * counted_steps(False) / max(prof["step_launches"], 1)
     peak, peak_src = hbm_peak()
     achieved = alg / (step_us * 1e-6) / 1e9
     key = f"step_N{N}_{'indirect' if args.indirect else 'direct'}_B{B}"
-    loop_gbs = alg / (ms / K * 1e-3) / 1e9
+    loop_gbs = algorithmic_bytes_per_step(N, args.indirect) * (counted / world) / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": committed_traffic(key), "kernel": "skyjo::step_kernel", "kernel_us": step_us,
                 "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
@@ -288,7 +308,6 @@ def run_ours(args, rank, local_rank, world):
                 "loop_frac": loop_gbs / peak,
                 "loop_frac_note": "same algorithmic bytes / whole timed loop (refill deals and stats included): "
                                   "a lower bound of the step kernel's fraction inside the loop"}
-    stats = env.stats(all_reduce=world > 1)
     env.check()
 
     # the same env-steps as multi-step launches (rollout_kernel: state in registers across 8 steps, every
@@ -302,6 +321,7 @@ def run_ours(args, rank, local_rank, world):
             reps = max(1, min(K, 1024) // T)
             for _ in range(2):
                 env.rollout_random(T, ro)
+            env.clear_stats()
             barrier()
             ev0.record()
             for _ in range(reps):
@@ -313,13 +333,14 @@ def run_ours(args, rank, local_rank, world):
             rms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(rms, op=dist.ReduceOp.MAX)
+            rcounted = counted_steps()
             rms = float(rms.item()) / (reps * T)
             env.profile_begin()
             for _ in range(reps):
                 env.rollout_random(T, ro)
             rp = env.profile_end()
             env.check()
-            rollout = {"value": B * world / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms,
+            rollout = {"value": rcounted / (rms * 1e-3 * reps * T), "unit": UNIT, "ms_per_step": rms,
                        "kernel": "skyjo::rollout_kernel", "env_steps_per_launch": 8, "rollout_len": T,
                        "kernel_us_per_env_step": 1e3 * rp["step_ms"] / (reps * T),
                        "hbm_bytes_written_per_env_step": D + 28,
@@ -351,6 +372,7 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout,
+            "counted_env_steps": counted, "counted_frac": counted_frac,
             "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")},
         }
         print(json.dumps(line), flush=True)
@@ -368,7 +390,7 @@ def run_e2e(args, env, dev, rank, world):
     N, B, T = args.players, args.envs, args.e2e_steps
     D = env.obs_len
     kw = dict(num_envs=B, num_players=N, observe_other_player_indirect=args.indirect, device=dev,
-              seed=args.seed + 1, first_global_env_id=rank * B)
+              seed=args.seed + 1, first_global_env_id=rank * B, auto_reset=args.reset)
     Tw = 3
     # record a legal action sequence on the device (untimed), then replay it from pinned host memory
     rec = BatchedSkyjoEnv(**kw)
@@ -390,6 +412,7 @@ def run_e2e(args, env, dev, rank, world):
     rew_h = torch.empty((B, N), dtype=torch.float64).pin_memory()
     for t in range(Tw):
         e.step_host(acts[t], obs_h, mask_h, agent_h, done_h, rew_h)
+    e.clear_stats()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -399,14 +422,14 @@ def run_e2e(args, env, dev, rank, world):
     dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    st = e.stats()
+    st = e.stats(all_reduce=world > 1)       # the timed steps only
     e.check()
     assert st["illegal"] == 0, "replayed actions must be legal"
     # bytes that cross the link per step (csrc/skyjo_hostio.cuh): obs rows as they are, mask + agent + done as
     # one packed word per env, a 4-byte count, and one {env, N rewards} entry per episode that ended
-    ended_per_step = (st["episodes"] + st["truncated"]) / float(T + Tw)
+    ended_per_step = (st["episodes"] + st["truncated"]) / float(T * world)
     d2h = B * (D + 4) + 4 + int(ended_per_step * (8 + 8 * N))
-    return {"value": B * world * T / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": B,
+    return {"value": st["steps"] / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": B,
             "d2h_bytes_per_step": d2h, "steps": T,
             "host_buffer_bytes_filled_per_step": B * (D + 26 + 1 + 1 + 8 * N),
             "api": "skyjo_step_host (C ABI) via BatchedSkyjoEnv.step_host, pinned host buffers: obs int8[B,D], "
@@ -424,6 +447,8 @@ def main():
     ap.add_argument("--indirect", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--preroll", type=int, default=640)
+    ap.add_argument("--reset", default="next_step", choices=["same_step", "next_step"],
+                    help="auto-reset mode (SKYJO_RESET_*): next_step = phase-locked, reset slots are not counted")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--rollout-steps", type=int, default=64, help="rollout length T of the multi-step path (0 = skip)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="CPU-seconds of oracle work (baseline sample)")

@@ -913,10 +913,11 @@ int skyjo_check(SkyjoHandle *h, void *stream) {
     CU(cudaMemcpyAsync(&flag, h->st.errflag, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     if (flag) {
-        snprintf(g_err, sizeof(g_err), "device consistency flag 0x%x:%s%s%s", flag,
+        snprintf(g_err, sizeof(g_err), "device consistency flag 0x%x:%s%s%s%s", flag,
                  (flag & ERR_NEXT_NOT_READY) ? " next episode was not dealt in time" : "",
                  (flag & ERR_BAD_DECK) ? " injected deck outside -2..12 or >15 copies of a value" : "",
-                 (flag & ERR_BAD_FLIPS) ? " injected flips invalid" : "");
+                 (flag & ERR_BAD_FLIPS) ? " injected flips invalid" : "",
+                 (flag & ERR_ASSIST) ? " warp assist missed a rare event" : "");
         return SKYJO_E_STATE;
     }
     return SKYJO_OK;

@@ -42,6 +42,18 @@ struct Outcome {
 };
 constexpr uint32_t PF_KEEP = 0xFFFFFFFFu;
 
+// Results the WARP computed for this env before env_step ran (device only, skyjo_step.cuh
+// warp_assist): the two rare events whose scalar code is long -- end-of-game scoring (N rows) and
+// the discard-only histogram an in-game reshuffle needs in direct mode (12 N slots) -- are executed
+// by one or two lanes of a warp while the other thirty wait.  The kernels hand such an env's rows
+// to lanes 0..N-1, one row each, and pass the reduced results in here.
+struct Assist {
+    int scored;  // 1: rewards and final scores of the ending game are stored, the fields below are valid
+    int raw_sum, winner_raw, fin_raw, penalised, refunds, winner;
+    int has_dh;   // 1: dh = the 15-bin histogram of the discard pile alone
+    uint64_t dh;
+};
+
 SKYJO_HD double sk_dadd(double a, double b) {
 #if defined(__CUDA_ARCH__)
     return __dadd_rn(a, b);
@@ -182,8 +194,11 @@ SKYJO_HD void store_env(U128 *planes, long long Bpad, long long e, const Env<N> 
 // One env-step for env e: SkyjoGame.act + rewards + (on episode end) auto-reset install.
 // `s` holds the loaded state and is updated in place; the caller stores it back.  With POLICY
 // the action is the uniform legal choice selected by `policy_rnd` = policy_random(seed, env, t).
-template <int N, bool IND, bool POLICY>
-SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int action, uint32_t policy_rnd = 0u) {
+// With ASSIST the caller guarantees `as` carries the results of every rare event this step runs
+// into (a missing one raises ERR_ASSIST); without it (host build, tests/hostsim) the scalar code runs.
+template <int N, bool IND, bool POLICY, bool ASSIST = false>
+SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int action, uint32_t policy_rnd = 0u,
+                          const Assist *as = nullptr) {
     Outcome oc;
     oc.done_code = SKYJO_RUNNING;
     oc.act_class = -1;
@@ -238,53 +253,64 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
         if (hidden == 0) {
             // ---- game over (skyjo.py:350-356): score, penalty, rewards -----------------------
             oc.done_code = SKYJO_DONE_GAME_OVER;
-            int raw[N];
-            int mn = 1 << 30, refunds = 0, raw_sum = 0;
-#pragma unroll
-            for (int q = 0; q < N; ++q) {
-                const Row &r = s.row[q];
-                uint32_t v[3];
-                row_cards(r, v);  // hidden cards count at their true value (skyjo.py:488-493)
-                raw[q] = score12(v);
-                mn = raw[q] < mn ? raw[q] : mn;
-                raw_sum += raw[q];
-                refunds += (int)sk_popc(row_flags(r));
-            }
-            int fin_raw = raw[0];
-#pragma unroll
-            for (int q = 1; q < N; ++q)
-                if (q == cur) fin_raw = raw[q];
-            const bool penalised = mn != fin_raw;  // skyjo.py:496
-            double score[N];
-#pragma unroll
-            for (int q = 0; q < N; ++q) {
-                score[q] = (double)raw[q];
-                if (penalised && q == cur) score[q] = sk_dmul(score[q], p.score_penalty);
-            }
-            // skyjo_env.py:307-311
-            const double mean = sk_ddiv(np_sum<N>(score), (double)N);
-            int winner = 0;
-            double best = score[0];
-#pragma unroll
-            for (int q = 0; q < N; ++q) {
-                double r = sk_dadd(sk_dadd(-score[q], mean), p.mean_reward);
-                if (p.reward_refunded != 0.0)
-                    r = sk_dadd(r, sk_dmul((double)sk_popc(row_flags(s.row[q])), p.reward_refunded));
-                p.reward[e * N + q] = r;
-                p.final_score[e * N + q] = score[q];
-                if (score[q] < best) {
-                    best = score[q];
-                    winner = q;
-                }
-            }
             oc.scored = 1;
             oc.ep_steps = (int)step + 1;
-            oc.raw_sum = raw_sum;
-            oc.winner_raw = mn;
-            oc.fin_raw = fin_raw;
-            oc.penalised = penalised ? 1 : 0;
-            oc.refunds = refunds;
-            oc.winner = winner;
+            if (ASSIST) {
+                // scored by the warp (warp_assist): rewards and final scores are already in memory
+                if (!as->scored) sk_flag(p.st.errflag, ERR_ASSIST);
+                oc.raw_sum = as->raw_sum;
+                oc.winner_raw = as->winner_raw;
+                oc.fin_raw = as->fin_raw;
+                oc.penalised = as->penalised;
+                oc.refunds = as->refunds;
+                oc.winner = as->winner;
+            } else {
+                int raw[N];
+                int mn = 1 << 30, refunds = 0, raw_sum = 0;
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    const Row &r = s.row[q];
+                    uint32_t v[3];
+                    row_cards(r, v);  // hidden cards count at their true value (skyjo.py:488-493)
+                    raw[q] = score12(v);
+                    mn = raw[q] < mn ? raw[q] : mn;
+                    raw_sum += raw[q];
+                    refunds += (int)sk_popc(row_flags(r));
+                }
+                int fin_raw = raw[0];
+#pragma unroll
+                for (int q = 1; q < N; ++q)
+                    if (q == cur) fin_raw = raw[q];
+                const bool penalised = mn != fin_raw;  // skyjo.py:496
+                double score[N];
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    score[q] = (double)raw[q];
+                    if (penalised && q == cur) score[q] = sk_dmul(score[q], p.score_penalty);
+                }
+                // skyjo_env.py:307-311
+                const double mean = sk_ddiv(np_sum<N>(score), (double)N);
+                int winner = 0;
+                double best = score[0];
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    double r = sk_dadd(sk_dadd(-score[q], mean), p.mean_reward);
+                    if (p.reward_refunded != 0.0)
+                        r = sk_dadd(r, sk_dmul((double)sk_popc(row_flags(s.row[q])), p.reward_refunded));
+                    p.reward[e * N + q] = r;
+                    p.final_score[e * N + q] = score[q];
+                    if (score[q] < best) {
+                        best = score[q];
+                        winner = q;
+                    }
+                }
+                oc.raw_sum = raw_sum;
+                oc.winner_raw = mn;
+                oc.fin_raw = fin_raw;
+                oc.penalised = penalised ? 1 : 0;
+                oc.refunds = refunds;
+                oc.winner = winner;
+            }
             oc.starter0 = (((hdr >> HDR_STARTER_SH) & 0xF) == 0) ? 1 : 0;
         } else {
             uint32_t code;
@@ -295,7 +321,10 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
                 if (n_draw == 0) {
                     // reshuffle the whole discard pile into a new draw pile (:361-365)
                     uint64_t dh = hist;
-                    if (!IND) {  // direct-mode hist also counts the open table cards
+                    if (!IND && ASSIST) {
+                        if (!as->has_dh) sk_flag(p.st.errflag, ERR_ASSIST);
+                        dh = as->dh;
+                    } else if (!IND) {  // direct-mode hist also counts the open table cards
 #pragma unroll
                         for (int q = 0; q < N; ++q) {
                             const Row &r = s.row[q];

@@ -271,6 +271,6 @@ struct RolloutParams {
     int bulk_ok;     // every slice 16-byte aligned -> TMA bulk stores
 };
 
-enum : uint32_t { ERR_NEXT_NOT_READY = 1, ERR_BAD_DECK = 2, ERR_BAD_FLIPS = 4 };
+enum : uint32_t { ERR_NEXT_NOT_READY = 1, ERR_BAD_DECK = 2, ERR_BAD_FLIPS = 4, ERR_ASSIST = 8 };
 
 }  // namespace skyjo

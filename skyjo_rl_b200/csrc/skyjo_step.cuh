@@ -29,6 +29,14 @@ namespace skyjo {
 #ifndef SKYJO_STEP_WARPS_MID
 #define SKYJO_STEP_WARPS_MID 28
 #endif
+// player count from which the warp assist (below) pays: at N <= 5 scoring N rows is short and
+// reshuffles do not occur, so its per-step test costs more than it saves (measured: N=4 +2 %, N=8 -17 %)
+#ifndef SKYJO_ASSIST_MIN_N
+#define SKYJO_ASSIST_MIN_N 6
+#endif
+#ifndef SKYJO_PF_LANES
+#define SKYJO_PF_LANES 1
+#endif
 #define STEP_WARPS_PER_SM(N) ((N) <= 5 ? SKYJO_STEP_WARPS_SMALL : ((N) <= 8 ? SKYJO_STEP_WARPS_MID : 12))
 #define STEP_MIN_CTAS(N) ((STEP_WARPS_PER_SM(N) * 32) / TILE)
 
@@ -110,6 +118,110 @@ __device__ __forceinline__ bool install_next_step(int auto_reset, uint64_t hdr, 
     return auto_reset && next_hidden == 0u && !(hdr & (HDR_PHASE | HDR_TERMINATED));
 }
 
+// ---- warp assist for the rare, long events ---------------------------------------------------------
+// End-of-game scoring (skyjo.py:477-498 + skyjo_env.py:293-312: N rows of 12 cards, float64 rewards)
+// and the discard-only histogram of an in-game reshuffle in direct mode (12 N table slots) hit about
+// one env in 130 / 330 per step, i.e. one or two lanes of a third of the warps, and their scalar code
+// is 350 - 1500 instructions that the other thirty lanes sit through (14 % of the N=4 kernel's
+// instructions, 42 % at N=8: profiles/).  Here the warp does them together: the env's rows go
+// through `scratch` (>= 16 N bytes of the warp's staging tile, not yet in use) to lanes 0..N-1, one
+// row per lane, and reductions bring the results back to the owning lane, which hands them to
+// env_step<.., ASSIST = true>.  The arithmetic (order of the float64 sums included) is that of the
+// scalar code in skyjo_core.cuh, which the host build and tests/hostsim keep using.
+template <int N, bool IND, bool POLICY>
+__device__ __forceinline__ void warp_assist(const StepParams &p, const Env<N> &s, long long e, bool valid, int action,
+                                            uint32_t policy_rnd, int lane, uint8_t *scratch, Assist &as) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    as.scored = 0;
+    as.has_dh = 0;
+    const uint64_t hdr = s.hdr;
+    const int cur = (int)(hdr >> HDR_CUR_SH) & 0xF;
+    uint32_t w0c = s.row[0].w0;
+#pragma unroll
+    for (int q = 1; q < N; ++q)
+        if (q == cur) w0c = s.row[q].w0;
+    const uint32_t hidden = w0c & 0xFFFu;
+    // the conditions under which env_step reaches the two events (same-phase test, legality, skyjo.py:350, :361)
+    const bool draws = valid && !(hdr & (HDR_PHASE | HDR_TERMINATED)) && (POLICY || action == 24 || action == 25);
+    const bool over = draws && hidden == 0u;
+    const bool from_pile = POLICY ? bounded(policy_rnd, 2u) == 0u : action == 24;
+    const bool resh = !IND && draws && hidden != 0u && from_pile && ((uint32_t)(hdr >> HDR_NDRAW_SH) & 0xFFu) == 0u;
+    unsigned need = __ballot_sync(FULL, over || resh);
+    uint4 *sc4 = reinterpret_cast<uint4 *>(scratch);
+    while (need) {  // warp-uniform
+        const int L = __ffs(need) - 1;
+        need &= need - 1u;
+        if (lane == L) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) sc4[k] = make_uint4(s.row[k].w0, s.row[k].w1, s.row[k].w2, s.row[k].w3);
+        }
+        __syncwarp();
+        const bool act = lane < N;
+        const uint4 t = sc4[act ? lane : 0];
+        __syncwarp();
+        const Row mine = {t.x, t.y, t.z, t.w};
+        const int is_over = __shfl_sync(FULL, (int)over, L);
+        if (is_over) {
+            const int curL = __shfl_sync(FULL, cur, L);
+            uint32_t v[3];
+            row_cards(mine, v);  // hidden cards count at their true value (skyjo.py:488-493)
+            const int raw = score12(v);
+            const int ref = (int)sk_popc(row_flags(mine));
+            const int mn = __reduce_min_sync(FULL, act ? raw : 0x7FFFFFFF);
+            const int raw_sum = __reduce_add_sync(FULL, act ? raw : 0);
+            const int refunds = __reduce_add_sync(FULL, act ? ref : 0);
+            const int fin_raw = __shfl_sync(FULL, raw, curL);
+            const bool penalised = mn != fin_raw;  // skyjo.py:496
+            double sc = (double)raw;
+            if (penalised && lane == curL) sc = sk_dmul(sc, p.score_penalty);
+            double a[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) a[q] = __shfl_sync(FULL, sc, q);
+            const double mean = sk_ddiv(np_sum<N>(a), (double)N);  // skyjo_env.py:307-311
+            int winner = 0;
+            double best = a[0];
+#pragma unroll
+            for (int q = 1; q < N; ++q)
+                if (a[q] < best) {
+                    best = a[q];
+                    winner = q;
+                }
+            if (act) {
+                double r = sk_dadd(sk_dadd(-sc, mean), p.mean_reward);
+                if (p.reward_refunded != 0.0) r = sk_dadd(r, sk_dmul((double)ref, p.reward_refunded));
+                const long long eL = e - lane + L;
+                p.reward[eL * N + lane] = r;
+                p.final_score[eL * N + lane] = sc;
+            }
+            if (lane == L) {
+                as.scored = 1;
+                as.raw_sum = raw_sum;
+                as.winner_raw = mn;
+                as.fin_raw = fin_raw;
+                as.penalised = penalised ? 1 : 0;
+                as.refunds = refunds;
+                as.winner = winner;
+            }
+        } else {
+            // open table cards of my row, as histogram increments (skyjo.py:241-246 count_players_cards)
+            uint64_t c = 0;
+            if (act) {
+                const uint32_t open = ~(row_hidden(mine) | cols_to_slots(row_flags(mine))) & 0xFFFu;
+#pragma unroll
+                for (uint32_t sl = 0; sl < 12; ++sl)
+                    if ((open >> sl) & 1u) c += hist_one((row_byte(mine, sl) + 2u) & 0xFFu);
+            }
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) c += __shfl_down_sync(FULL, c, off);  // N <= 12 lanes hold data
+            const uint64_t tot = __shfl_sync(FULL, c, 0);
+            if (lane == L) {
+                as.has_dh = 1;
+                as.dh = s.hist - tot;
+            }
+        }
+    }
+}
+
 // Stores one warp's 32-row slice of an output tile: one TMA bulk store issued by lane 0 when the
 // slice is complete and 16-byte aligned, a byte loop otherwise (ragged last tile).
 __device__ __forceinline__ void store_warp_slice(const uint8_t *s_src, int8_t *g_dst, uint32_t row_bytes,
@@ -155,6 +267,16 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     // L2 prefetch of the planes of the tile `pf_dist` CTAs ahead (about one wave of resident CTAs):
     // by the time that CTA is scheduled its 1 + N plane loads hit L2 instead of waiting for DRAM.
     // One bulk-prefetch instruction per plane (512 B = the tile's slice), issued by lane 0.
+#if SKYJO_PF_LANES
+    if (p.pf_dist > 0 && lane <= N) {  // lane q prefetches the slice of plane q
+        const long long pt = (long long)blockIdx.x + p.pf_dist;
+        if (pt < (long long)gridDim.x)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p.st.planes + (pt + p.tile_off) * TILE +
+                                                                            (long long)lane * p.Bpad),
+                         "r"((uint32_t)(TILE * 16))
+                         : "memory");
+    }
+#else
     if (p.pf_dist > 0 && lane == 0) {
         const long long pt = (long long)blockIdx.x + p.pf_dist;
         if (pt < (long long)gridDim.x) {
@@ -166,6 +288,7 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
                              : "memory");
         }
     }
+#endif
     // the policy's random word depends only on (seed, env, t): drawn before the wait, so CTAs that
     // were scheduled early have work to do while the previous step's grid drains
     uint32_t policy_rnd = 0u;
@@ -181,8 +304,11 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     int act_class = -1;
     uint32_t dirty_rows = 0, pf_new = PF_KEEP;
     int done_code = SKYJO_RUNNING;
+    constexpr bool ASSIST = N >= SKYJO_ASSIST_MIN_N;
+    Assist as;
+    if (ASSIST) warp_assist<N, IND, POLICY>(p, s, e, valid, action, policy_rnd, lane, smem + (size_t)warp * 32 * D, as);
     if (valid) {
-        const Outcome oc = env_step<N, IND, POLICY>(p, e, s, action, policy_rnd);
+        const Outcome oc = env_step<N, IND, POLICY, ASSIST>(p, e, s, action, policy_rnd, &as);
         dirty_rows = oc.dirty_rows;
         pf_new = oc.pf_new;
         done_code = oc.done_code;
@@ -281,16 +407,13 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N))
     const unsigned long long genv = p.first_env + (unsigned long long)e;
     s_stats[warp][lane] = 0;
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    if (p.pf_dist > 0 && lane == 0) {
+    if (p.pf_dist > 0 && lane <= N) {
         const long long pt = (long long)blockIdx.x + p.pf_dist;
-        if (pt < (long long)gridDim.x) {
-            const U128 *src = p.st.planes + pt * TILE;
-#pragma unroll
-            for (int q = 0; q <= N; ++q)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src + (long long)q * p.Bpad),
-                             "r"((uint32_t)(TILE * 16))
-                             : "memory");
-        }
+        if (pt < (long long)gridDim.x)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p.st.planes + pt * TILE +
+                                                                            (long long)lane * p.Bpad),
+                         "r"((uint32_t)(TILE * 16))
+                         : "memory");
     }
     uint32_t policy_rnd = policy_random(p.seed, genv, p.t);
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -313,8 +436,11 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N))
         }
         int act_class = -1, done_code = SKYJO_RUNNING;
         uint32_t pf_new = PF_KEEP;
+        constexpr bool ASSIST = N >= SKYJO_ASSIST_MIN_N;
+        Assist as;
+        if (ASSIST) warp_assist<N, IND, true>(p, s, e, valid, 0, policy_rnd, lane, smem + (size_t)warp * 32 * D, as);
         if (valid) {
-            const Outcome oc = env_step<N, IND, true>(p, e, s, 0, policy_rnd);
+            const Outcome oc = env_step<N, IND, true, ASSIST>(p, e, s, 0, policy_rnd, &as);
             dirty_all |= oc.dirty_rows;
             pf_new = oc.pf_new;
             done_code = oc.done_code;
