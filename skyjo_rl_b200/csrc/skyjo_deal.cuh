@@ -33,7 +33,9 @@ struct DealParams {
     const uint8_t *flips;  // injected flips uint8[B,N,2] or null
 };
 
-// Deck: uint8_t get(int i); void set(int i, uint8_t v); uint32_t word(int w)  (i < 152, w < 38)
+// Deck: uint8_t get(int i); void set(int i, uint8_t v); uint32_t word(int w)  (i < 152, w < 38);
+//       get_at(ibase, off) / set_at(ibase, off, v) = get / set(ibase + off) with ibase a multiple of 4
+//       (possibly negative) and off a compile-time constant
 template <class Deck>
 SKYJO_HD void deal_one(const DealParams &p, long long e, uint32_t slot, Deck &deck) {
     const int N = p.N;
@@ -50,24 +52,31 @@ SKYJO_HD void deal_one(const DealParams &p, long long e, uint32_t slot, Deck &de
         // one group ahead of the swaps that consume them, so that the ten dependent rounds of a
         // block overlap those of its neighbours and the shared-memory round trips of the previous
         // group's swaps (one thread's 38 blocks back to back were 60 % of the kernel's latency).
-        constexpr int DEAL_ILP = 4, NBLK = (SKYJO_DECK - 1 + 3) / 4;
+        constexpr int DEAL_ILP = 4, NBLK = (SKYJO_DECK - 1 + 3) / 4, GROUPS = (NBLK + DEAL_ILP - 1) / DEAL_ILP;
         U4 cur[DEAL_ILP], nxt[DEAL_ILP];
 #pragma unroll
         for (int u = 0; u < DEAL_ILP; ++u) cur[u] = rng_block(p.seed, genv, PURPOSE_DEAL, ep, (uint32_t)u);
+        // Group t swaps i = ibase + 21 - c, c = 0..15, with ibase = 128 - 16 t a multiple of 16: the
+        // deck accessor resolves (ibase, constant offset) with one address computation per group, so
+        // only j is addressed dynamically; the loop stays rolled (unrolled, its 130 KB of straight-line
+        // code run once per warp were instruction-fetch bound).
 #pragma unroll 1
-        for (int g0 = 0; g0 < NBLK; g0 += DEAL_ILP) {
+        for (int t = 0; t < GROUPS; ++t) {
+            const int ibase = SKYJO_DECK - 1 - 21 - 4 * DEAL_ILP * t;
 #pragma unroll
-            for (int u = 0; u < DEAL_ILP; ++u) nxt[u] = rng_block(p.seed, genv, PURPOSE_DEAL, ep, (uint32_t)(g0 + DEAL_ILP + u));
+            for (int u = 0; u < DEAL_ILP; ++u)
+                nxt[u] = rng_block(p.seed, genv, PURPOSE_DEAL, ep, (uint32_t)(DEAL_ILP * (t + 1) + u));
 #pragma unroll
             for (int u = 0; u < DEAL_ILP; ++u) {
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
-                    const int i = SKYJO_DECK - 1 - (4 * (g0 + u) + w);
+                    const int off = 21 - (4 * u + w);
+                    const int i = ibase + off;
                     if (i >= 1) {
                         const uint32_t r = w == 0 ? cur[u].x : w == 1 ? cur[u].y : w == 2 ? cur[u].z : cur[u].w;
                         const int j = (int)bounded(r, (uint32_t)(i + 1));
-                        const uint8_t a = deck.get(i), b = deck.get(j);
-                        deck.set(i, b);
+                        const uint8_t a = deck.get_at(ibase, off), b = deck.get(j);
+                        deck.set_at(ibase, off, b);
                         deck.set(j, a);
                     }
                 }
@@ -232,6 +241,12 @@ struct SmemDeck {  // [word][thread] layout
     __device__ __forceinline__ void set(int i, uint8_t v) { base[((i >> 2) * DEAL_THREADS + tid) * 4 + (i & 3)] = v; }
     __device__ __forceinline__ uint32_t word(int w) const {
         return reinterpret_cast<const uint32_t *>(base)[w * DEAL_THREADS + tid];
+    }
+    __device__ __forceinline__ uint8_t get_at(int ibase, int off) const {
+        return base[((ibase >> 2) * DEAL_THREADS + tid) * 4 + ((off >> 2) * DEAL_THREADS * 4 + (off & 3))];
+    }
+    __device__ __forceinline__ void set_at(int ibase, int off, uint8_t v) {
+        base[((ibase >> 2) * DEAL_THREADS + tid) * 4 + ((off >> 2) * DEAL_THREADS * 4 + (off & 3))] = v;
     }
 };
 

@@ -34,9 +34,6 @@ namespace skyjo {
 #ifndef SKYJO_ASSIST_MIN_N
 #define SKYJO_ASSIST_MIN_N 6
 #endif
-#ifndef SKYJO_PF_LANES
-#define SKYJO_PF_LANES 1
-#endif
 #define STEP_WARPS_PER_SM(N) ((N) <= 5 ? SKYJO_STEP_WARPS_SMALL : ((N) <= 8 ? SKYJO_STEP_WARPS_MID : 12))
 #define STEP_MIN_CTAS(N) ((STEP_WARPS_PER_SM(N) * 32) / TILE)
 
@@ -267,16 +264,6 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     // L2 prefetch of the planes of the tile `pf_dist` CTAs ahead (about one wave of resident CTAs):
     // by the time that CTA is scheduled its 1 + N plane loads hit L2 instead of waiting for DRAM.
     // One bulk-prefetch instruction per plane (512 B = the tile's slice), issued by lane 0.
-#if SKYJO_PF_LANES
-    if (p.pf_dist > 0 && lane <= N) {  // lane q prefetches the slice of plane q
-        const long long pt = (long long)blockIdx.x + p.pf_dist;
-        if (pt < (long long)gridDim.x)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p.st.planes + (pt + p.tile_off) * TILE +
-                                                                            (long long)lane * p.Bpad),
-                         "r"((uint32_t)(TILE * 16))
-                         : "memory");
-    }
-#else
     if (p.pf_dist > 0 && lane == 0) {
         const long long pt = (long long)blockIdx.x + p.pf_dist;
         if (pt < (long long)gridDim.x) {
@@ -288,7 +275,6 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
                              : "memory");
         }
     }
-#endif
     // the policy's random word depends only on (seed, env, t): drawn before the wait, so CTAs that
     // were scheduled early have work to do while the previous step's grid drains
     uint32_t policy_rnd = 0u;
@@ -407,13 +393,16 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N))
     const unsigned long long genv = p.first_env + (unsigned long long)e;
     s_stats[warp][lane] = 0;
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    if (p.pf_dist > 0 && lane <= N) {
+    if (p.pf_dist > 0 && lane == 0) {
         const long long pt = (long long)blockIdx.x + p.pf_dist;
-        if (pt < (long long)gridDim.x)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p.st.planes + pt * TILE +
-                                                                            (long long)lane * p.Bpad),
-                         "r"((uint32_t)(TILE * 16))
-                         : "memory");
+        if (pt < (long long)gridDim.x) {
+            const U128 *src = p.st.planes + pt * TILE;
+#pragma unroll
+            for (int q = 0; q <= N; ++q)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src + (long long)q * p.Bpad),
+                             "r"((uint32_t)(TILE * 16))
+                             : "memory");
+        }
     }
     uint32_t policy_rnd = policy_random(p.seed, genv, p.t);
     asm volatile("griddepcontrol.wait;\n" ::: "memory");

@@ -38,6 +38,8 @@ struct ArrayDeck {
     uint8_t b[152];
     uint8_t get(int i) const { return b[i]; }
     void set(int i, uint8_t v) { b[i] = v; }
+    uint8_t get_at(int ibase, int off) const { return b[ibase + off]; }
+    void set_at(int ibase, int off, uint8_t v) { b[ibase + off] = v; }
     uint32_t word(int w) const {
         uint32_t x;
         memcpy(&x, b + 4 * w, 4);
