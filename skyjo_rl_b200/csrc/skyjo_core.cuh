@@ -101,31 +101,39 @@ SKYJO_HD double np_sum(const double (&a)[N]) {
 }
 
 // sample one card code from a packed histogram (sampling without replacement of the
-// reshuffled pile, DESIGN.md "in-game reshuffle"); idx < total
+// reshuffled pile, DESIGN.md "in-game reshuffle"): the smallest code c with
+// cnt[0] + .. + cnt[c] > idx; idx < total <= 150.  Branch-free SWAR instead of a 14-step scan (the
+// scan was 95 warp-instructions per draw-slot step at N=8, run by one or two lanes of most warps):
+// the 16 nibbles are spread to bytes, byte-wise inclusive prefix sums come from multiplications by
+// 0x01010101 (no carries: every prefix <= 150), and "prefix > idx" is the carry out of
+// prefix + (255 - idx), assembled per byte from the 7-bit sum and the two top bits.
 SKYJO_HD uint32_t hist_take(uint64_t &h, uint32_t idx) {
-    uint32_t code = 14;
-    bool found = false;
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    uint32_t b0 = spread4(lo & 0xFFFFu);
+    const uint32_t b1 = spread4(lo >> 16), b2 = spread4(hi & 0xFFFFu), b3 = spread4(hi >> 16);
+    b0 = (b0 & 0x00FFFFFFu) + ((b0 >> 24) << 20);  // bin 2 is 8 bits wide: byte 2 += 16 * byte 3, byte 3 = 0
+    uint32_t p[4];
+    p[0] = b0 * 0x01010101u;
+    p[1] = b1 * 0x01010101u + (p[0] >> 24) * 0x01010101u;
+    p[2] = b2 * 0x01010101u + (p[1] >> 24) * 0x01010101u;
+    p[3] = b3 * 0x01010101u + (p[2] >> 24) * 0x01010101u;
+    const uint32_t k = 255u - idx, kl = (k & 0x7Fu) * 0x01010101u, m7 = (k & 0x80u) ? 0xFFFFFFFFu : 0u;
+    uint32_t n = 16u;  // index of the first byte whose prefix exceeds idx
 #pragma unroll
-    for (uint32_t c = 0; c < 14; ++c) {
-        const uint32_t cnt = hist_get(h, c);
-        if (!found) {
-            if (idx < cnt) {
-                code = c;
-                found = true;
-            } else {
-                idx -= cnt;
-            }
-        }
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t x = p[w], sm = (x & 0x7F7F7F7Fu) + kl;
+        n -= sk_popc(((x & sm) | ((x | sm) & m7)) & 0x80808080u);
     }
+    const uint32_t code = n - (n > 2u ? 1u : 0u);  // byte 3 is the empty upper half of bin 2
     h -= hist_one(code);
     return code;
 }
 
 SKYJO_HD uint32_t hist_total(uint64_t h) {
-    uint32_t t = 0;
-#pragma unroll
-    for (uint32_t c = 0; c < 15; ++c) t += hist_get(h, c);
-    return t;
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    const uint32_t a = (lo & 0x0F0F0F0Fu) + ((lo >> 4) & 0x0F0F0F0Fu), b = (hi & 0x0F0F0F0Fu) + ((hi >> 4) & 0x0F0F0F0Fu);
+    // nibble 3 of lo is the high half of the 8-bit bin 2: it weighs 16, the nibble sum counted it once
+    return (((a + b) * 0x01010101u) >> 24) + 15u * ((lo >> 12) & 0xFu);
 }
 
 // raw (unpenalised) score of 12 true card values given as three words of int8:
@@ -481,11 +489,6 @@ struct ObsWords {
     uint32_t s[NW];
     uint32_t m[7];
 };
-
-SKYJO_HD uint32_t spread4(uint32_t x) {  // 4 nibbles (16 bits) -> 4 bytes
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    return (x | (x << 4)) & 0x0F0F0F0Fu;
-}
 
 // collect_observation (skyjo.py:148-199) of `observer` on state s.
 template <int N, bool IND>

@@ -135,6 +135,11 @@ SKYJO_HD uint32_t cols_to_slots(uint32_t f) {
 }
 // 4 bits -> 4 bytes of 0/1
 SKYJO_HD uint32_t bits01(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
+// 4 nibbles (16 bits) -> 4 bytes
+SKYJO_HD uint32_t spread4(uint32_t x) {
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    return (x | (x << 4)) & 0x0F0F0F0Fu;
+}
 // 4 bits -> 4 bytes of 0x00/0xFF
 SKYJO_HD uint32_t bitsFF(uint32_t x) { return bits01(x) * 0xFFu; }
 // per-byte (code - 2) of four codes 0..14 (no borrow between bytes)
