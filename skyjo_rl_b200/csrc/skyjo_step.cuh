@@ -22,20 +22,37 @@
 
 namespace skyjo {
 
-// resident warps per SM the step kernel is compiled for (caps registers: 2048 / warps per thread)
+// resident warps per SM the kernels are compiled for (caps registers: 2048 / warps per thread).
+// Measured on B200 (tools/variants.py, next-step reset, 2^20 / 2^22 envs): N <= 5: 32 warps (64
+// registers) beat 28 / 24; N = 6: 28; N = 7: 24; N = 8: 22 (88 registers; 28: +7 %, 24: +0.6 %,
+// 20: +4.5 %); N >= 9: 12 (16 / 20 / 24: +4 / +3 / +23 %).  The rollout kernel keeps the state live
+// across its steps and likes one notch fewer warps at N = 8.
 #ifndef SKYJO_STEP_WARPS_SMALL
 #define SKYJO_STEP_WARPS_SMALL 32
 #endif
 #ifndef SKYJO_STEP_WARPS_MID
-#define SKYJO_STEP_WARPS_MID 28
+#define SKYJO_STEP_WARPS_MID(N) ((N) == 6 ? 28 : ((N) == 7 ? 24 : 22))
+#endif
+#ifndef SKYJO_STEP_WARPS_LARGE
+#define SKYJO_STEP_WARPS_LARGE 12
+#endif
+#ifndef SKYJO_ROLLOUT_WARPS_SMALL
+#define SKYJO_ROLLOUT_WARPS_SMALL 32
+#endif
+#ifndef SKYJO_ROLLOUT_WARPS_MID
+#define SKYJO_ROLLOUT_WARPS_MID(N) ((N) == 6 ? 28 : ((N) == 7 ? 24 : 20))
 #endif
 // player count from which the warp assist (below) pays: at N <= 5 scoring N rows is short and
-// reshuffles do not occur, so its per-step test costs more than it saves (measured: N=4 +2 %, N=8 -17 %)
+// reshuffles do not occur, so its per-step test costs more than it saves (measured: N=4 +2 %,
+// N=5 +-0, N=8 -17 %)
 #ifndef SKYJO_ASSIST_MIN_N
 #define SKYJO_ASSIST_MIN_N 6
 #endif
-#define STEP_WARPS_PER_SM(N) ((N) <= 5 ? SKYJO_STEP_WARPS_SMALL : ((N) <= 8 ? SKYJO_STEP_WARPS_MID : 12))
+#define STEP_WARPS_PER_SM(N) ((N) <= 5 ? SKYJO_STEP_WARPS_SMALL : ((N) <= 8 ? SKYJO_STEP_WARPS_MID(N) : SKYJO_STEP_WARPS_LARGE))
+#define ROLLOUT_WARPS_PER_SM(N) \
+    ((N) <= 5 ? SKYJO_ROLLOUT_WARPS_SMALL : ((N) <= 8 ? SKYJO_ROLLOUT_WARPS_MID(N) : SKYJO_STEP_WARPS_LARGE))
 #define STEP_MIN_CTAS(N) ((STEP_WARPS_PER_SM(N) * 32) / TILE)
+#define ROLLOUT_MIN_CTAS(N) ((ROLLOUT_WARPS_PER_SM(N) * 32) / TILE)
 
 constexpr int WARPS = TILE / 32;
 
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
 // are pure overhead; this kernel removes them.  Rewards keep the [B, N] "last finished episode,
 // cleared by the next step" semantics of the single-step kernel (skyjo_env.py:242-252).
 template <int N, bool IND>
-__global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N))
+__global__ void __launch_bounds__(TILE, ROLLOUT_MIN_CTAS(N))
     rollout_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RolloutParams r) {
     using OW = ObsWords<N, IND>;
     constexpr int D = OW::D;
