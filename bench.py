@@ -302,9 +302,10 @@ def run_ours(args, rank, local_rank, world):
                 "traffic": committed_traffic(key), "kernel": "skyjo::step_kernel", "kernel_us": step_us,
                 "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                 "deal_kernel_share": prof["deal_ms"] / max(prof["deal_ms"] + prof["step_ms"], 1e-9),
-                "note": "kernel_us = mean duration of a full-batch step launch running alone (per-launch CUDA events, "
-                        "refill deals in stream order); the timed loop behind `value` steps the batch as 4 env ranges "
-                        "on 4 streams, so that one range's launch ramp / tail is covered by the others",
+                "note": "kernel_us = mean duration of a full-batch step launch on one stream: CUDA events bracket every window "
+                        "of 8 back-to-back launches between two refill deals (no event between launches; the deals, "
+                        "in stream order, are timed by their own pairs); the timed loop behind `value` steps the batch "
+                        "as 4 env ranges on 4 streams, so that one range's launch ramp / tail is covered by the others",
                 "loop_frac": loop_gbs / peak,
                 "loop_frac_note": "same algorithmic bytes / whole timed loop (refill deals and stats included): "
                                   "a lower bound of the step kernel's fraction inside the loop"}

@@ -83,8 +83,15 @@ struct SkyjoHandle {
     int pf_dist;  // L2 prefetch distance of the step kernel, in tiles
     // optional per-kernel event timing (skyjo_step_random_profile)
     bool profiling;
+    // Profiling mode: CUDA-event pairs on the launching stream.  A pair brackets one deal / rollout
+    // launch, or one WINDOW of back-to-back single-step launches (up to 8, the launches between two
+    // refill deals) -- no event between them, because an event record between two 45 us kernels
+    // adds ~6 us to each pair (measured against ncu's gpu__time_duration) and breaks their
+    // programmatic dependent launch, i.e. it times something the step loop never runs.
     std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
     std::vector<int> prof_kind;            // 0 step kernel, 1 deal kernel
+    std::vector<int> prof_count;           // launches the pair covers
+    bool prof_window_open = false;
     // skyjo_step_host wire staging (skyjo_hostio.cuh), created on first use
     bool hostio_ready;
     cudaStream_t copy_stream;
@@ -109,11 +116,17 @@ static void prof_begin(SkyjoHandle *h, int kind, cudaStream_t s) {
     h->prof_events.push_back(a);
     h->prof_events.push_back(b);
     h->prof_kind.push_back(kind);
+    h->prof_count.push_back(1);
     cudaEventRecord(a, s);
 }
 static void prof_end(SkyjoHandle *h, cudaStream_t s) {
     if (!h->profiling) return;
     cudaEventRecord(h->prof_events.back(), s);
+}
+static void prof_close_window(SkyjoHandle *h, cudaStream_t s) {
+    if (!h->profiling || !h->prof_window_open) return;
+    cudaEventRecord(h->prof_events.back(), s);
+    h->prof_window_open = false;
 }
 
 static thread_local char g_err[512] = "";
@@ -485,13 +498,22 @@ static int step_once(SkyjoHandle *h, const void *actions, int dtype, bool policy
     StepParams p = make_params(h);
     p.actions = actions;
     p.action_dtype = dtype;
-    prof_begin(h, 0, s);
+    if (h->profiling) {
+        if (!h->prof_window_open) {
+            prof_begin(h, 0, s);
+            h->prof_window_open = true;
+        } else {
+            h->prof_count.back() += 1;
+        }
+    }
     cudaError_t le = kStep[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, policy, s);
-    prof_end(h, s);
     CU(le);
     h->launches += 1;
     h->t += 1;
-    if (++h->steps_since_deal >= deal_period(h, policy)) return close_window(h, s, policy);
+    if (++h->steps_since_deal >= deal_period(h, policy)) {
+        prof_close_window(h, s);
+        return close_window(h, s, policy);
+    }
     return SKYJO_OK;
 }
 
@@ -576,6 +598,7 @@ int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream) {
         if (rc) return rc;
     }
     // every call ends with its window closed (the deal may still be running on deal_stream)
+    prof_close_window(h, s);
     if (h->steps_since_deal > 0) return close_window(h, s, true);
     return SKYJO_OK;
 }
@@ -638,13 +661,15 @@ int skyjo_profile_end(SkyjoHandle *h, void *stream, double *step_ms, double *dea
         float ms = 0.f;
         if (se == cudaSuccess && cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]) == cudaSuccess) {
             sum[h->prof_kind[i]] += ms;
-            cnt[h->prof_kind[i]] += 1;
+            cnt[h->prof_kind[i]] += h->prof_count[i];
         }
         cudaEventDestroy(h->prof_events[2 * i]);
         cudaEventDestroy(h->prof_events[2 * i + 1]);
     }
     h->prof_events.clear();
     h->prof_kind.clear();
+    h->prof_count.clear();
+    h->prof_window_open = false;
     CU(se);
     *step_ms = sum[0];
     *deal_ms = sum[1];
