@@ -298,8 +298,12 @@ def run_ours(args, rank, local_rank, world):
     achieved = alg / (step_us * 1e-6) / 1e9
     key = f"step_N{N}_{'indirect' if args.indirect else 'direct'}_B{B}"
     loop_gbs = algorithmic_bytes_per_step(N, args.indirect) * (counted / world) / (ms * 1e-3) / 1e9
+    traffic = committed_traffic(key)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": committed_traffic(key), "kernel": "skyjo::step_kernel", "kernel_us": step_us,
+                "traffic": traffic, "kernel": "skyjo::step_kernel", "kernel_us": step_us,
+                # the int8 planes move fewer bytes than SURVEY 8(d)'s accounting (80 B of planes read per 4-player
+                # env-step instead of 120, ...): the DRAM bytes ncu measured per launch over the same kernel time
+                "traffic_frac": (traffic / (step_us * 1e-6) / 1e9 / peak) if traffic else None,
                 "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                 "deal_kernel_share": prof["deal_ms"] / max(prof["deal_ms"] + prof["step_ms"], 1e-9),
                 "note": "kernel_us = mean duration of a full-batch step launch on one stream: CUDA events bracket every window "
