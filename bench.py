@@ -353,6 +353,11 @@ def run_ours(args, rank, local_rank, world):
                                "mask, agent and done are stored into slice t of [T,B,...] rollout tensors"}
             del ro
 
+    # BASELINE config 4: the action-mask MLP policy (library GEMMs) consuming obs / mask in place
+    policy_rollout = None
+    if args.policy_steps > 0 and rank == 0:
+        policy_rollout = run_policy_rollout(args, dev)
+
     # end to end through the host-buffer C-ABI entry
     e2e = None
     if args.e2e_steps > 0:
@@ -377,13 +382,57 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout,
-            "counted_env_steps": counted, "counted_frac": counted_frac,
+            "counted_env_steps": counted, "counted_frac": counted_frac, "policy_rollout": policy_rollout,
             "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_policy_rollout(args, dev):
+    """a torch MLP (TorchActionMaskModel restated, skyjo_rl_b200/policy.py) reads the env's obs /
+    mask tensors in place, the fused masked-softmax-sample kernel writes uint8 actions, skyjo_step consumes them.
+    One GPU; the GEMMs are ATen's (library code), so this is a consumer-side figure, not a kernel claim."""
+    import torch
+
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    from skyjo_rl_b200.policy import ActionMaskPolicy
+
+    N, T = args.players, args.policy_steps
+    B = min(args.envs, args.policy_envs)
+    env = BatchedSkyjoEnv(num_envs=B, num_players=N, observe_other_player_indirect=args.indirect, device=dev,
+                          seed=args.seed + 2)
+    env.reset()
+    torch.manual_seed(0)
+    policy = ActionMaskPolicy(env.obs_len).to(dev)
+    ptr = (env.observations.data_ptr(), env.action_mask.data_ptr())
+    obs = {"observations": env.observations, "action_mask": env.action_mask}
+
+    def steps(n):
+        with torch.no_grad():
+            for _ in range(n):
+                act, _ = env.sample_actions(policy(obs))
+                env.step(act)
+
+    steps(8)
+    env.clear_stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    steps(T)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1)
+    st = env.stats()
+    env.check()
+    assert ptr == (env.observations.data_ptr(), env.action_mask.data_ptr()), "obs / mask must be consumed in place"
+    assert st["illegal"] == 0
+    env.close()
+    return {"value": st["steps"] / (ms * 1e-3), "unit": UNIT, "envs": B, "steps": T, "ms_per_step": ms / T,
+            "policy": "ActionMaskPolicy 2x256 tanh + value branch, fp32 (ATen GEMMs), fused masked-softmax-sample kernel",
+            "zero_copy": True, "reset": "same_step"}
 
 
 def run_e2e(args, env, dev, rank, world):
@@ -456,6 +505,8 @@ def main():
                     help="auto-reset mode (SKYJO_RESET_*): next_step = phase-locked, reset slots are not counted")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--rollout-steps", type=int, default=64, help="rollout length T of the multi-step path (0 = skip)")
+    ap.add_argument("--policy-steps", type=int, default=24, help="steps of the torch-policy rollout, config 4 (0 = skip)")
+    ap.add_argument("--policy-envs", type=int, default=1 << 18)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="CPU-seconds of oracle work (baseline sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--python-reference", action="store_true")
