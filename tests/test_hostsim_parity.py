@@ -93,3 +93,16 @@ def test_hostsim_illegal_and_truncation():
         env2.step_random(1)
         trunc += int((env2.done_code == 3).sum())
     assert trunc == 3 * B and env2.stats()["truncated"] == 3 * B
+
+
+@pytest.mark.parametrize("N,indirect,mode,max_steps,B,T", [
+    (2, False, 1, 0, 48, 260), (3, False, 2, 0, 48, 330), (3, True, 0, 0, 40, 200),
+    (4, False, 2, 45, 40, 300), (5, False, 1, 60, 32, 300), (2, True, 2, 33, 48, 260),
+])
+def test_hostsim_external_actions_match_the_oracle_model(N, indirect, mode, max_steps, B, T):
+    # random external actions with 2 % illegal ones, all three reset modes, truncation on and off
+    from parity_util import external_actions_rollout
+    seen, st = external_actions_rollout(HostSimEnv, N, indirect, mode, max_steps, B, T)
+    assert seen[2] > 0 and st["illegal"] > 0
+    if max_steps:
+        assert seen[3] > 0
