@@ -237,208 +237,208 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
         return oc;
     }
 
-    do {
-    if (reset_slot) break;
-    Row a = s.row[0];
+    do {  // skipped in a reset slot
+        if (reset_slot) break;
+        Row a = s.row[0];
 #pragma unroll
-    for (int q = 1; q < N; ++q)
-        if (q == cur) a = s.row[q];
-    uint32_t hidden = row_hidden(a), flags = row_flags(a);
-    const uint32_t legal = legal_bits(hidden, flags, place_phase);
-    const unsigned long long genv = p.first_env + (unsigned long long)e;
-    if (POLICY) action = policy_select(policy_rnd, legal);
-    const bool is_legal = action >= 0 && action < 26 && ((legal >> action) & 1u);
-    uint32_t step = (uint32_t)(hdr & HDR_STEP_MASK);
-    const uint8_t *deck = p.st.deck + (((hdr & HDR_SLOT) ? p.Bpad : 0ll) + e) * PILE_ROW;
+        for (int q = 1; q < N; ++q)
+            if (q == cur) a = s.row[q];
+        uint32_t hidden = row_hidden(a), flags = row_flags(a);
+        const uint32_t legal = legal_bits(hidden, flags, place_phase);
+        const unsigned long long genv = p.first_env + (unsigned long long)e;
+        if (POLICY) action = policy_select(policy_rnd, legal);
+        const bool is_legal = action >= 0 && action < 26 && ((legal >> action) & 1u);
+        uint32_t step = (uint32_t)(hdr & HDR_STEP_MASK);
+        const uint8_t *deck = p.st.deck + (((hdr & HDR_SLOT) ? p.Bpad : 0ll) + e) * PILE_ROW;
 
-    if (!is_legal) {
-        // TerminateIllegalWrapper(illegal_reward=-1), skyjo_env.py:23
-        oc.done_code = SKYJO_DONE_ILLEGAL;
+        if (!is_legal) {
+            // TerminateIllegalWrapper(illegal_reward=-1), skyjo_env.py:23
+            oc.done_code = SKYJO_DONE_ILLEGAL;
 #pragma unroll
-        for (int q = 0; q < N; ++q) p.reward[e * N + q] = (q == cur) ? -1.0 : 0.0;
-    } else if (!place_phase) {
-        oc.act_class = action - 24;
-        if (hidden == 0) {
-            // ---- game over (skyjo.py:350-356): score, penalty, rewards -----------------------
-            oc.done_code = SKYJO_DONE_GAME_OVER;
-            oc.scored = 1;
-            oc.ep_steps = (int)step + 1;
-            if (ASSIST) {
-                // scored by the warp (warp_assist): rewards and final scores are already in memory
-                if (!as->scored) sk_flag(p.st.errflag, ERR_ASSIST);
-                oc.raw_sum = as->raw_sum;
-                oc.winner_raw = as->winner_raw;
-                oc.fin_raw = as->fin_raw;
-                oc.penalised = as->penalised;
-                oc.refunds = as->refunds;
-                oc.winner = as->winner;
-            } else {
-                int raw[N];
-                int mn = 1 << 30, refunds = 0, raw_sum = 0;
+            for (int q = 0; q < N; ++q) p.reward[e * N + q] = (q == cur) ? -1.0 : 0.0;
+        } else if (!place_phase) {
+            oc.act_class = action - 24;
+            if (hidden == 0) {
+                // ---- game over (skyjo.py:350-356): score, penalty, rewards -----------------------
+                oc.done_code = SKYJO_DONE_GAME_OVER;
+                oc.scored = 1;
+                oc.ep_steps = (int)step + 1;
+                if (ASSIST) {
+                    // scored by the warp (warp_assist): rewards and final scores are already in memory
+                    if (!as->scored) sk_flag(p.st.errflag, ERR_ASSIST);
+                    oc.raw_sum = as->raw_sum;
+                    oc.winner_raw = as->winner_raw;
+                    oc.fin_raw = as->fin_raw;
+                    oc.penalised = as->penalised;
+                    oc.refunds = as->refunds;
+                    oc.winner = as->winner;
+                } else {
+                    int raw[N];
+                    int mn = 1 << 30, refunds = 0, raw_sum = 0;
 #pragma unroll
-                for (int q = 0; q < N; ++q) {
-                    const Row &r = s.row[q];
-                    uint32_t v[3];
-                    row_cards(r, v);  // hidden cards count at their true value (skyjo.py:488-493)
-                    raw[q] = score12(v);
-                    mn = raw[q] < mn ? raw[q] : mn;
-                    raw_sum += raw[q];
-                    refunds += (int)sk_popc(row_flags(r));
-                }
-                int fin_raw = raw[0];
-#pragma unroll
-                for (int q = 1; q < N; ++q)
-                    if (q == cur) fin_raw = raw[q];
-                const bool penalised = mn != fin_raw;  // skyjo.py:496
-                double score[N];
-#pragma unroll
-                for (int q = 0; q < N; ++q) {
-                    score[q] = (double)raw[q];
-                    if (penalised && q == cur) score[q] = sk_dmul(score[q], p.score_penalty);
-                }
-                // skyjo_env.py:307-311
-                const double mean = sk_ddiv(np_sum<N>(score), (double)N);
-                int winner = 0;
-                double best = score[0];
-#pragma unroll
-                for (int q = 0; q < N; ++q) {
-                    double r = sk_dadd(sk_dadd(-score[q], mean), p.mean_reward);
-                    if (p.reward_refunded != 0.0)
-                        r = sk_dadd(r, sk_dmul((double)sk_popc(row_flags(s.row[q])), p.reward_refunded));
-                    p.reward[e * N + q] = r;
-                    p.final_score[e * N + q] = score[q];
-                    if (score[q] < best) {
-                        best = score[q];
-                        winner = q;
+                    for (int q = 0; q < N; ++q) {
+                        const Row &r = s.row[q];
+                        uint32_t v[3];
+                        row_cards(r, v);  // hidden cards count at their true value (skyjo.py:488-493)
+                        raw[q] = score12(v);
+                        mn = raw[q] < mn ? raw[q] : mn;
+                        raw_sum += raw[q];
+                        refunds += (int)sk_popc(row_flags(r));
                     }
-                }
-                oc.raw_sum = raw_sum;
-                oc.winner_raw = mn;
-                oc.fin_raw = fin_raw;
-                oc.penalised = penalised ? 1 : 0;
-                oc.refunds = refunds;
-                oc.winner = winner;
-            }
-            oc.starter0 = (((hdr >> HDR_STARTER_SH) & 0xF) == 0) ? 1 : 0;
-        } else {
-            uint32_t code;
-            if (action == 24) {
-                // ---- draw from the draw pile (skyjo.py:359-366) -------------------------------
-                uint32_t n_draw = (uint32_t)(hdr >> HDR_NDRAW_SH) & 0xFFu;
-                uint64_t *lazy = reinterpret_cast<uint64_t *>(const_cast<uint8_t *>(deck) + LAZY_OFF);
-                if (n_draw == 0) {
-                    // reshuffle the whole discard pile into a new draw pile (:361-365)
-                    uint64_t dh = hist;
-                    if (!IND && ASSIST) {
-                        if (!as->has_dh) sk_flag(p.st.errflag, ERR_ASSIST);
-                        dh = as->dh;
-                    } else if (!IND) {  // direct-mode hist also counts the open table cards
+                    int fin_raw = raw[0];
 #pragma unroll
-                        for (int q = 0; q < N; ++q) {
-                            const Row &r = s.row[q];
-                            const uint32_t open = ~(row_hidden(r) | cols_to_slots(row_flags(r))) & 0xFFFu;
-                            for (uint32_t sl = 0; sl < 12; ++sl)
-                                if ((open >> sl) & 1u) dh -= hist_one((row_byte(r, sl) + 2u) & 0xFFu);
+                    for (int q = 1; q < N; ++q)
+                        if (q == cur) fin_raw = raw[q];
+                    const bool penalised = mn != fin_raw;  // skyjo.py:496
+                    double score[N];
+#pragma unroll
+                    for (int q = 0; q < N; ++q) {
+                        score[q] = (double)raw[q];
+                        if (penalised && q == cur) score[q] = sk_dmul(score[q], p.score_penalty);
+                    }
+                    // skyjo_env.py:307-311
+                    const double mean = sk_ddiv(np_sum<N>(score), (double)N);
+                    int winner = 0;
+                    double best = score[0];
+#pragma unroll
+                    for (int q = 0; q < N; ++q) {
+                        double r = sk_dadd(sk_dadd(-score[q], mean), p.mean_reward);
+                        if (p.reward_refunded != 0.0)
+                            r = sk_dadd(r, sk_dmul((double)sk_popc(row_flags(s.row[q])), p.reward_refunded));
+                        p.reward[e * N + q] = r;
+                        p.final_score[e * N + q] = score[q];
+                        if (score[q] < best) {
+                            best = score[q];
+                            winner = q;
                         }
                     }
-                    const uint32_t total = hist_total(dh);
-                    const uint32_t ep = running_episode(p.st, e, hdr);
-                    const uint32_t q8 = (uint32_t)(hdr >> HDR_Q_SH) & (uint32_t)HDR_Q_MASK;
-                    U4 r0 = rng_block(p.seed, genv, PURPOSE_RESHUFFLE, ep, (q8 << 16) | total);
-                    uint64_t left = dh;
-                    const uint32_t e0 = hist_take(left, bounded(r0.x, total));
-                    hist = hist - dh + hist_one(e0);  // new discard pile = [e0]
-                    hdr = (hdr & ~((0xFFull << HDR_TOP_SH) | (HDR_Q_MASK << HDR_Q_SH))) |
-                          ((uint64_t)(e0 + 1u) << HDR_TOP_SH) | ((uint64_t)((q8 + 1u) & (uint32_t)HDR_Q_MASK) << HDR_Q_SH) |
-                          HDR_LAZY;
-                    n_draw = total - 1u;
-                    U4 r1 = rng_block(p.seed, genv, PURPOSE_RESHUFFLE, ep, (q8 << 16) | n_draw);
-                    code = hist_take(left, bounded(r1.x, n_draw));
-                    *lazy = left;
-                    oc.reshuffled = 1;
-                } else if (hdr & HDR_LAZY) {
-                    uint64_t left = *lazy;
-                    const uint32_t ep = running_episode(p.st, e, hdr);
-                    const uint32_t q8 = ((uint32_t)(hdr >> HDR_Q_SH) - 1u) & (uint32_t)HDR_Q_MASK;
-                    U4 r1 = rng_block(p.seed, genv, PURPOSE_RESHUFFLE, ep, (q8 << 16) | n_draw);
-                    code = hist_take(left, bounded(r1.x, n_draw));
-                    *lazy = left;
-                } else {
-                    // the top card was prefetched into the header; fetch the one below it for the
-                    // next draw (its value is only needed when the header is stored)
-                    code = hdr_pf_get(hdr);
-                    oc.pf_new = n_draw > 1u ? (uint32_t)deck[12 * N + n_draw - 2u] : 0u;
+                    oc.raw_sum = raw_sum;
+                    oc.winner_raw = mn;
+                    oc.fin_raw = fin_raw;
+                    oc.penalised = penalised ? 1 : 0;
+                    oc.refunds = refunds;
+                    oc.winner = winner;
                 }
-                n_draw -= 1u;
-                hdr = (hdr & ~(0xFFull << HDR_NDRAW_SH)) | ((uint64_t)n_draw << HDR_NDRAW_SH);
+                oc.starter0 = (((hdr >> HDR_STARTER_SH) & 0xF) == 0) ? 1 : 0;
             } else {
-                // ---- take the discard top (skyjo.py:370) ----------------------------------------
-                const uint32_t top = (uint32_t)(hdr >> HDR_TOP_SH) & 0xFu;
-                const uint32_t second = (uint32_t)(hdr >> HDR_SECOND_SH) & 0xFu;
-                code = top - 1u;
-                hist -= hist_one(code);
-                hdr = (hdr & ~(0xFFull << HDR_TOP_SH)) | ((uint64_t)second << HDR_TOP_SH);
+                uint32_t code;
+                if (action == 24) {
+                    // ---- draw from the draw pile (skyjo.py:359-366) -------------------------------
+                    uint32_t n_draw = (uint32_t)(hdr >> HDR_NDRAW_SH) & 0xFFu;
+                    uint64_t *lazy = reinterpret_cast<uint64_t *>(const_cast<uint8_t *>(deck) + LAZY_OFF);
+                    if (n_draw == 0) {
+                        // reshuffle the whole discard pile into a new draw pile (:361-365)
+                        uint64_t dh = hist;
+                        if (!IND && ASSIST) {
+                            if (!as->has_dh) sk_flag(p.st.errflag, ERR_ASSIST);
+                            dh = as->dh;
+                        } else if (!IND) {  // direct-mode hist also counts the open table cards
+#pragma unroll
+                            for (int q = 0; q < N; ++q) {
+                                const Row &r = s.row[q];
+                                const uint32_t open = ~(row_hidden(r) | cols_to_slots(row_flags(r))) & 0xFFFu;
+                                for (uint32_t sl = 0; sl < 12; ++sl)
+                                    if ((open >> sl) & 1u) dh -= hist_one((row_byte(r, sl) + 2u) & 0xFFu);
+                            }
+                        }
+                        const uint32_t total = hist_total(dh);
+                        const uint32_t ep = running_episode(p.st, e, hdr);
+                        const uint32_t q8 = (uint32_t)(hdr >> HDR_Q_SH) & (uint32_t)HDR_Q_MASK;
+                        U4 r0 = rng_block(p.seed, genv, PURPOSE_RESHUFFLE, ep, (q8 << 16) | total);
+                        uint64_t left = dh;
+                        const uint32_t e0 = hist_take(left, bounded(r0.x, total));
+                        hist = hist - dh + hist_one(e0);  // new discard pile = [e0]
+                        hdr = (hdr & ~((0xFFull << HDR_TOP_SH) | (HDR_Q_MASK << HDR_Q_SH))) |
+                              ((uint64_t)(e0 + 1u) << HDR_TOP_SH) | ((uint64_t)((q8 + 1u) & (uint32_t)HDR_Q_MASK) << HDR_Q_SH) |
+                              HDR_LAZY;
+                        n_draw = total - 1u;
+                        U4 r1 = rng_block(p.seed, genv, PURPOSE_RESHUFFLE, ep, (q8 << 16) | n_draw);
+                        code = hist_take(left, bounded(r1.x, n_draw));
+                        *lazy = left;
+                        oc.reshuffled = 1;
+                    } else if (hdr & HDR_LAZY) {
+                        uint64_t left = *lazy;
+                        const uint32_t ep = running_episode(p.st, e, hdr);
+                        const uint32_t q8 = ((uint32_t)(hdr >> HDR_Q_SH) - 1u) & (uint32_t)HDR_Q_MASK;
+                        U4 r1 = rng_block(p.seed, genv, PURPOSE_RESHUFFLE, ep, (q8 << 16) | n_draw);
+                        code = hist_take(left, bounded(r1.x, n_draw));
+                        *lazy = left;
+                    } else {
+                        // the top card was prefetched into the header; fetch the one below it for the
+                        // next draw (its value is only needed when the header is stored)
+                        code = hdr_pf_get(hdr);
+                        oc.pf_new = n_draw > 1u ? (uint32_t)deck[12 * N + n_draw - 2u] : 0u;
+                    }
+                    n_draw -= 1u;
+                    hdr = (hdr & ~(0xFFull << HDR_NDRAW_SH)) | ((uint64_t)n_draw << HDR_NDRAW_SH);
+                } else {
+                    // ---- take the discard top (skyjo.py:370) ----------------------------------------
+                    const uint32_t top = (uint32_t)(hdr >> HDR_TOP_SH) & 0xFu;
+                    const uint32_t second = (uint32_t)(hdr >> HDR_SECOND_SH) & 0xFu;
+                    code = top - 1u;
+                    hist -= hist_one(code);
+                    hdr = (hdr & ~(0xFFull << HDR_TOP_SH)) | ((uint64_t)second << HDR_TOP_SH);
+                }
+                hdr = (hdr & ~(0xFull << HDR_HAND_SH)) | ((uint64_t)code << HDR_HAND_SH) | HDR_PHASE;
             }
-            hdr = (hdr & ~(0xFull << HDR_HAND_SH)) | ((uint64_t)code << HDR_HAND_SH) | HDR_PHASE;
-        }
-    } else {
-        // ---- place (skyjo.py:376-427) --------------------------------------------------------
-        const uint32_t hand = (uint32_t)(hdr >> HDR_HAND_SH) & 0xFu;
-        uint32_t top = (uint32_t)(hdr >> HDR_TOP_SH) & 0xFu;
-        uint32_t second = top;
-        const bool swap = action < 12;
-        const uint32_t sl = swap ? (uint32_t)action : (uint32_t)action - 12u;
-        const bool was_hidden = (hidden >> sl) & 1u;
-        const uint32_t tc = (row_byte(a, sl) + 2u) & 0xFFu;  // code of the card in the slot
-        int sum24 = (int)row_sum24(a);
-        if (swap) {  // :389-395 the old card (even if hidden) goes to the discard pile
-            oc.act_class = 2;
-            top = tc + 1u;
-            if (IND || was_hidden) hist += hist_one(tc);
-            if (!IND) hist += hist_one(hand);
-            row_set_byte(a, sl, (hand - 2u) & 0xFFu);
-            sum24 += (int)hand - 2 - (was_hidden ? 0 : (int)tc - 2);
-        } else {  // :396-404 discard the hand card and reveal the slot
-            oc.act_class = 3;
-            top = hand + 1u;
-            hist += hist_one(hand);
-            if (!IND) hist += hist_one(tc);
-            sum24 += (int)tc - 2;
-        }
-        hidden &= ~(1u << sl);
-        // column removal (:431-469): only the touched column can newly qualify
-        const uint32_t col = sl / 3u;
-        const uint32_t c3 = row_col(a, col);
-        const uint32_t b0 = c3 & 0xFFu;
-        if (c3 == b0 * 0x010101u && ((hidden >> (3u * col)) & 7u) == 0u && !((flags >> col) & 1u)) {
-            const uint32_t c0 = (b0 + 2u) & 0xFFu;
-            if (!IND) hist -= 3ull * hist_one(c0);
-            hist += 3ull * hist_one(2u);  // three zeros go to the discard pile (:454-458)
-            top = 3u;
-            second = 3u;
-            flags |= 1u << col;
-            row_remove_col(a, col);
-            sum24 -= 3 * ((int)c0 - 2);
-        }
-        row_set_meta(a, hidden, flags, (uint32_t)sum24);
-        const int nxt = (cur + 1 == N) ? 0 : cur + 1;
-        hdr = (hdr & ~((0xFull << HDR_CUR_SH) | HDR_PHASE | (0xFFFull << HDR_HAND_SH))) |
-              ((uint64_t)nxt << HDR_CUR_SH) | ((uint64_t)HAND_NONE << HDR_HAND_SH) |
-              ((uint64_t)top << HDR_TOP_SH) | ((uint64_t)second << HDR_SECOND_SH);
+        } else {
+            // ---- place (skyjo.py:376-427) --------------------------------------------------------
+            const uint32_t hand = (uint32_t)(hdr >> HDR_HAND_SH) & 0xFu;
+            uint32_t top = (uint32_t)(hdr >> HDR_TOP_SH) & 0xFu;
+            uint32_t second = top;
+            const bool swap = action < 12;
+            const uint32_t sl = swap ? (uint32_t)action : (uint32_t)action - 12u;
+            const bool was_hidden = (hidden >> sl) & 1u;
+            const uint32_t tc = (row_byte(a, sl) + 2u) & 0xFFu;  // code of the card in the slot
+            int sum24 = (int)row_sum24(a);
+            if (swap) {  // :389-395 the old card (even if hidden) goes to the discard pile
+                oc.act_class = 2;
+                top = tc + 1u;
+                if (IND || was_hidden) hist += hist_one(tc);
+                if (!IND) hist += hist_one(hand);
+                row_set_byte(a, sl, (hand - 2u) & 0xFFu);
+                sum24 += (int)hand - 2 - (was_hidden ? 0 : (int)tc - 2);
+            } else {  // :396-404 discard the hand card and reveal the slot
+                oc.act_class = 3;
+                top = hand + 1u;
+                hist += hist_one(hand);
+                if (!IND) hist += hist_one(tc);
+                sum24 += (int)tc - 2;
+            }
+            hidden &= ~(1u << sl);
+            // column removal (:431-469): only the touched column can newly qualify
+            const uint32_t col = sl / 3u;
+            const uint32_t c3 = row_col(a, col);
+            const uint32_t b0 = c3 & 0xFFu;
+            if (c3 == b0 * 0x010101u && ((hidden >> (3u * col)) & 7u) == 0u && !((flags >> col) & 1u)) {
+                const uint32_t c0 = (b0 + 2u) & 0xFFu;
+                if (!IND) hist -= 3ull * hist_one(c0);
+                hist += 3ull * hist_one(2u);  // three zeros go to the discard pile (:454-458)
+                top = 3u;
+                second = 3u;
+                flags |= 1u << col;
+                row_remove_col(a, col);
+                sum24 -= 3 * ((int)c0 - 2);
+            }
+            row_set_meta(a, hidden, flags, (uint32_t)sum24);
+            const int nxt = (cur + 1 == N) ? 0 : cur + 1;
+            hdr = (hdr & ~((0xFull << HDR_CUR_SH) | HDR_PHASE | (0xFFFull << HDR_HAND_SH))) |
+                  ((uint64_t)nxt << HDR_CUR_SH) | ((uint64_t)HAND_NONE << HDR_HAND_SH) |
+                  ((uint64_t)top << HDR_TOP_SH) | ((uint64_t)second << HDR_SECOND_SH);
 #pragma unroll
-        for (int q = 0; q < N; ++q)
-            if (q == cur) s.row[q] = a;
-        oc.dirty_rows |= 1u << cur;
-    }
-    if (oc.done_code == SKYJO_RUNNING) {
-        step = step + 1u < 0xFFFFu ? step + 1u : 0xFFFFu;
-        hdr = (hdr & ~HDR_STEP_MASK) | step;
-        if (p.max_steps > 0 && step >= (uint32_t)p.max_steps) {
-            oc.done_code = SKYJO_DONE_TRUNCATED;
-#pragma unroll
-            for (int q = 0; q < N; ++q) p.reward[e * N + q] = 0.0;
+            for (int q = 0; q < N; ++q)
+                if (q == cur) s.row[q] = a;
+            oc.dirty_rows |= 1u << cur;
         }
-    }
+        if (oc.done_code == SKYJO_RUNNING) {
+            step = step + 1u < 0xFFFFu ? step + 1u : 0xFFFFu;
+            hdr = (hdr & ~HDR_STEP_MASK) | step;
+            if (p.max_steps > 0 && step >= (uint32_t)p.max_steps) {
+                oc.done_code = SKYJO_DONE_TRUNCATED;
+#pragma unroll
+                for (int q = 0; q < N; ++q) p.reward[e * N + q] = 0.0;
+            }
+        }
     } while (0);
     // ---- episode end: install the pre-dealt next episode, defer it to the next slot, or freeze ----
     if (oc.done_code != SKYJO_RUNNING || reset_slot) {
