@@ -106,3 +106,8 @@ def test_hostsim_external_actions_match_the_oracle_model(N, indirect, mode, max_
     assert seen[2] > 0 and st["illegal"] > 0
     if max_steps:
         assert seen[3] > 0
+
+
+@pytest.mark.parametrize("N,B,T,mode", [(1, 1, 120, 2), (2, 31, 200, 2), (12, 3, 700, 2), (7, 20, 450, 2)])
+def test_hostsim_small_batches_in_next_step_mode(N, B, T, mode):
+    rng_rollout(HostSimEnv, N, False, 2.0, 1.0, 0.0, B, T, reset_mode=mode)
