@@ -353,6 +353,38 @@ def run_ours(args, rank, local_rank, world):
                                "mask, agent and done are stored into slice t of [T,B,...] rollout tensors"}
             del ro
 
+    # the other reset mode, same workload and timing rules, so that both figures come from one run
+    other = None
+    if args.other_reset_steps > 0:
+        mode2 = "same_step" if args.reset == "next_step" else "next_step"
+        env2 = BatchedSkyjoEnv(num_envs=B, num_players=N, observe_other_player_indirect=args.indirect,
+                               device=dev, seed=args.seed, first_global_env_id=rank * B, auto_reset=mode2)
+        env2.reset()
+        K2 = min(K, args.other_reset_steps)
+        env2.step_random(args.preroll)
+        env2.step_random(max(W, 3))
+        env2.clear_stats()
+        barrier()
+        ev0.record()
+        env2.step_random(K2)
+        ev1.record()
+        barrier()
+        ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        v2 = env2.stats_tensor()
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(v2)
+        c2 = int(v2[_lib.STAT_NAMES.index("steps")].item())
+        env2.clear_stats()
+        prof2 = env2.step_random_profile(min(K2, 256))
+        us2 = 1e3 * prof2["step_ms"] / max(prof2["step_launches"], 1)
+        alg2 = algorithmic_bytes_per_step(N, args.indirect) * int(env2.stats()["steps"]) / max(prof2["step_launches"], 1)
+        env2.check()
+        other = {"reset": mode2, "value": c2 / (float(ms2.item()) * 1e-3), "unit": UNIT, "steps": K2,
+                 "ms_per_step": float(ms2.item()) / K2, "kernel_us": us2, "frac": alg2 / (us2 * 1e-6) / 1e9 / peak}
+        env2.close()
+        del env2
+
     # BASELINE config 4: the action-mask MLP policy (library GEMMs) consuming obs / mask in place
     policy_rollout = None
     if args.policy_steps > 0 and rank == 0:
@@ -382,7 +414,8 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout,
-            "counted_env_steps": counted, "counted_frac": counted_frac, "policy_rollout": policy_rollout,
+            "counted_env_steps": counted, "counted_frac": counted_frac, "other_reset_mode": other,
+            "policy_rollout": policy_rollout,
             "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")},
         }
         print(json.dumps(line), flush=True)
@@ -505,6 +538,8 @@ def main():
                     help="auto-reset mode (SKYJO_RESET_*): next_step = phase-locked, reset slots are not counted")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--rollout-steps", type=int, default=64, help="rollout length T of the multi-step path (0 = skip)")
+    ap.add_argument("--other-reset-steps", type=int, default=1000,
+                    help="also time this many steps in the other auto-reset mode (0 = skip)")
     ap.add_argument("--policy-steps", type=int, default=24, help="steps of the torch-policy rollout, config 4 (0 = skip)")
     ap.add_argument("--policy-envs", type=int, default=1 << 18)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="CPU-seconds of oracle work (baseline sample)")

@@ -19,17 +19,17 @@ python bench.py --reset same_step --players 8 --envs 4194304 --steps 500 --warmu
 export SKYJO_RANGES=1
 # launch list of the timed loop (cold-cache, serialised per-launch times: shares only)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 730 -c 400 --csv --log-file $O/${T}_launches.csv \
-    python bench.py --steps 400 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 > /dev/null 2>&1
+    python bench.py --steps 400 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 --other-reset-steps 0 --policy-steps 0 > /dev/null 2>&1
 # full captures of the dominant kernels
 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 700 -c 2 -f -o $O/${T}_step_full \
-    python bench.py --steps 100 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 > /dev/null 2>&1
+    python bench.py --steps 100 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 --other-reset-steps 0 --policy-steps 0 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 4 -c 1 -f -o $O/${T}_rollout_full \
-    python bench.py --steps 16 --warmup 3 --preroll 320 --e2e-steps 0 --no-cpu-baseline --rollout-steps 16 > $O/${T}_rollout_ncu.log 2>&1
+    python bench.py --steps 16 --warmup 3 --preroll 320 --e2e-steps 0 --no-cpu-baseline --rollout-steps 16 --other-reset-steps 0 --policy-steps 0 > $O/${T}_rollout_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 1100 -c 2 -f -o $O/${T}_step_n8_full \
-    python bench.py --players 8 --envs 4194304 --preroll 1024 --steps 100 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 > /dev/null 2>&1
+    python bench.py --players 8 --envs 4194304 --preroll 1024 --steps 100 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 --other-reset-steps 0 --policy-steps 0 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:deal_kernel -s 20 -c 1 -f -o $O/${T}_deal_full \
-    python bench.py --steps 100 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 > /dev/null 2>&1
+    python bench.py --steps 100 --warmup 10 --e2e-steps 0 --no-cpu-baseline --rollout-steps 0 --other-reset-steps 0 --policy-steps 0 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:pack_host_kernel -s 2 -c 1 -f -o $O/${T}_pack_full \
-    python bench.py --steps 8 --warmup 3 --preroll 64 --e2e-steps 3 --no-cpu-baseline --rollout-steps 0 > /dev/null 2>&1
+    python bench.py --steps 8 --warmup 3 --preroll 64 --e2e-steps 3 --no-cpu-baseline --rollout-steps 0 --other-reset-steps 0 --policy-steps 0 > /dev/null 2>&1
 unset SKYJO_RANGES
 ls -la $O
