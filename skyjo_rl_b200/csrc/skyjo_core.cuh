@@ -19,6 +19,10 @@
 #include "skyjo_rng.cuh"
 #include "skyjo_state.cuh"
 
+#ifndef SKYJO_DRAW_SHORTCUT_MAX_N
+#define SKYJO_DRAW_SHORTCUT_MAX_N 4
+#endif
+
 namespace skyjo {
 
 template <int N>
@@ -246,7 +250,12 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
         uint32_t hidden = row_hidden(a), flags = row_flags(a);
         const uint32_t legal = legal_bits(hidden, flags, place_phase);
         const unsigned long long genv = p.first_env + (unsigned long long)e;
-        if (POLICY) action = policy_select(policy_rnd, legal);
+        // uniform over the legal actions; in the draw phase these are exactly {24, 25}, where the k-th set bit
+        // of policy_select is 24 + k (a warp-uniform shortcut when the batch is phase-locked)
+        // (small N only: from N = 5 the extra branch costs registers -- spills, +5 % kernel time at N = 8)
+        if (POLICY)
+            action = (N <= SKYJO_DRAW_SHORTCUT_MAX_N && !place_phase) ? 24 + (int)bounded(policy_rnd, 2u)
+                                                                      : policy_select(policy_rnd, legal);
         const bool is_legal = action >= 0 && action < 26 && ((legal >> action) & 1u);
         uint32_t step = (uint32_t)(hdr & HDR_STEP_MASK);
         const uint8_t *deck = p.st.deck + (((hdr & HDR_SLOT) ? p.Bpad : 0ll) + e) * PILE_ROW;
@@ -540,9 +549,15 @@ SKYJO_HD void encode_words(const Env<N> &s, int observer, ObsWords<N, IND> &o, u
     }
     // action mask, 26 bytes of 0/1
     if (observer_hidden) *observer_hidden = row_hidden(ob);
-    const uint32_t lb = legal_bits(row_hidden(ob), row_flags(ob), (s.hdr & HDR_PHASE) != 0);
+    if (N > SKYJO_DRAW_SHORTCUT_MAX_N || (s.hdr & HDR_PHASE)) {
+        const uint32_t lb = legal_bits(row_hidden(ob), row_flags(ob), (s.hdr & HDR_PHASE) != 0);
 #pragma unroll
-    for (int k = 0; k < 7; ++k) o.m[k] = bits01(lb >> (4 * k));
+        for (int k = 0; k < 7; ++k) o.m[k] = bits01(lb >> (4 * k));
+    } else {  // draw phase: actions 24 and 25 (skyjo.py:218-221), whatever the row
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o.m[k] = 0u;
+        o.m[6] = 0x00000101u;
+    }
 }
 
 // The aligned words a thread owns in its warp's slice of an output tile.  A warp's 32 rows

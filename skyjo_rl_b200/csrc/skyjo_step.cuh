@@ -23,8 +23,8 @@
 namespace skyjo {
 
 // resident warps per SM the kernels are compiled for (caps registers: 2048 / warps per thread).
-// Measured on B200 (tools/variants.py, next-step reset, 2^20 / 2^22 envs): N <= 5: 32 warps (64
-// registers) beat 28 / 24; N = 6: 28; N = 7: 24; N = 8: 22 (88 registers; 28: +7 %, 24: +0.6 %,
+// Measured on B200 (tools/variants.py, next-step reset, 2^20 / 2^22 envs): N <= 4: 32 warps (64
+// registers) beat 28 / 24; N = 5: 28 (-2.7 % vs 32, which spills); N = 6: 28; N = 7: 24; N = 8: 22 (88 registers; 28: +7 %, 24: +0.6 %,
 // 20: +4.5 %); N >= 9: 12 (16 / 20 / 24: +4 / +3 / +23 %).  The rollout kernel keeps the state live
 // across its steps and likes one notch fewer warps at N = 8.
 #ifndef SKYJO_STEP_WARPS_SMALL
@@ -48,7 +48,12 @@ namespace skyjo {
 #ifndef SKYJO_ASSIST_MIN_N
 #define SKYJO_ASSIST_MIN_N 6
 #endif
-#define STEP_WARPS_PER_SM(N) ((N) <= 5 ? SKYJO_STEP_WARPS_SMALL : ((N) <= 8 ? SKYJO_STEP_WARPS_MID(N) : SKYJO_STEP_WARPS_LARGE))
+#ifndef SKYJO_STEP_WARPS_5
+#define SKYJO_STEP_WARPS_5 28
+#endif
+#define STEP_WARPS_PER_SM(N) \
+    ((N) <= 4 ? SKYJO_STEP_WARPS_SMALL  \
+              : ((N) == 5 ? SKYJO_STEP_WARPS_5 : ((N) <= 8 ? SKYJO_STEP_WARPS_MID(N) : SKYJO_STEP_WARPS_LARGE)))
 #define ROLLOUT_WARPS_PER_SM(N) \
     ((N) <= 5 ? SKYJO_ROLLOUT_WARPS_SMALL : ((N) <= 8 ? SKYJO_ROLLOUT_WARPS_MID(N) : SKYJO_STEP_WARPS_LARGE))
 #define STEP_MIN_CTAS(N) ((STEP_WARPS_PER_SM(N) * 32) / TILE)
