@@ -375,8 +375,9 @@ int sk_rng_policy(uint64_t seed, uint64_t env, uint64_t t, const int8_t *mask26)
     for (int i = 0; i < 26; ++i) count += mask26[i] != 0;
     if (count == 0) return -1;
     uint32_t blk[4];
-    rng_block(seed, env, PURPOSE_POLICY, (uint32_t)t, (uint32_t)(t >> 32), blk);
-    int k = (int)bounded(blk[0], (uint32_t)count);
+    /* product protocol: one Philox block per four lockstep steps, step t takes word t & 3 */
+    rng_block(seed, env, PURPOSE_POLICY, (uint32_t)(t >> 2), (uint32_t)(t >> 34), blk);
+    int k = (int)bounded(blk[t & 3u], (uint32_t)count);
     for (int i = 0; i < 26; ++i)
         if (mask26[i] && k-- == 0) return i;
     return -1;

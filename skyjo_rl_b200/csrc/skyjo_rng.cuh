@@ -4,7 +4,7 @@
 // (Salmon et al., SC11) keyed by the user seed and counted by
 //   c0 = global_env[31:0]
 //   c1 = global_env[55:32] | purpose << 24
-//   c2, c3 = purpose-specific (episode, block) / (t_lo, t_hi)
+//   c2, c3 = purpose-specific (episode, block) / (lo, hi of t >> 2 for the policy, word t & 3)
 // so that an env's games depend only on (seed, global env id), never on batch size,
 // sharding or launch schedule.  Bounded integers use the multiply-shift map
 // floor(r * n / 2^32) (bias <= n / 2^32 < 4e-8 for n <= 150).
@@ -96,8 +96,19 @@ SKYJO_HD int nth_set_bit(uint32_t m, int k) {
 
 // random_admissible_policy.py:26-28: uniform over the legal actions.  The random word depends
 // only on (seed, env, t), so a kernel can draw it before the state has arrived.
+// One Philox block serves four consecutive lockstep steps: step t uses word t & 3 of the block counted
+// by t >> 2, so the multi-step rollout kernel draws one block per four env-steps (the ten rounds were 7 %
+// of its instructions).
+SKYJO_HD U4 policy_block(uint64_t seed, uint64_t env, uint64_t t) {
+    const uint64_t g = t >> 2;
+    return rng_block(seed, env, PURPOSE_POLICY, (uint32_t)g, (uint32_t)(g >> 32));
+}
+SKYJO_HD uint32_t policy_word(const U4 &b, uint64_t t) {
+    const uint32_t w = (uint32_t)t & 3u;
+    return w == 0u ? b.x : (w == 1u ? b.y : (w == 2u ? b.z : b.w));
+}
 SKYJO_HD uint32_t policy_random(uint64_t seed, uint64_t env, uint64_t t) {
-    return rng_block(seed, env, PURPOSE_POLICY, (uint32_t)t, (uint32_t)(t >> 32)).x;
+    return policy_word(policy_block(seed, env, t), t);
 }
 SKYJO_HD int policy_select(uint32_t rnd, uint32_t legal_bits) {
 #if defined(__CUDA_ARCH__)

@@ -426,7 +426,8 @@ __global__ void __launch_bounds__(TILE, ROLLOUT_MIN_CTAS(N))
                              : "memory");
         }
     }
-    uint32_t policy_rnd = policy_random(p.seed, genv, p.t);
+    U4 pblk = policy_block(p.seed, genv, p.t);  // one Philox block per four lockstep steps
+    uint32_t policy_rnd = policy_word(pblk, p.t);
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
     Env<N> s;
@@ -440,7 +441,9 @@ __global__ void __launch_bounds__(TILE, ROLLOUT_MIN_CTAS(N))
     long long lane_stat = 0;  // lane k accumulates statistics entry k over the K steps
     for (int k = 0; k < r.K; ++k) {
         if (k > 0) {
-            policy_rnd = policy_random(p.seed, genv, p.t + (unsigned long long)k);
+            const unsigned long long tk = p.t + (unsigned long long)k;
+            if ((tk & 3ull) == 0ull) pblk = policy_block(p.seed, genv, tk);  // warp-uniform
+            policy_rnd = policy_word(pblk, tk);
             // the staging tile is reused: the previous step's bulk stores must have read it
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
             __syncwarp();

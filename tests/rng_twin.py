@@ -55,8 +55,9 @@ def flips(seed, env, episode, num_players):
 
 def policy(seed, env, t, mask):
     legal = [i for i, m in enumerate(mask) if m]
-    blk = block(seed, env, PURPOSE_POLICY, t & M32, t >> 32)
-    return legal[bounded(blk[0], len(legal))]
+    g = t >> 2                      # one Philox block per four lockstep steps, step t takes word t & 3
+    blk = block(seed, env, PURPOSE_POLICY, g & M32, g >> 32)
+    return legal[bounded(blk[t & 3], len(legal))]
 
 
 def reshuffle(seed, env, episode, q, pile):
