@@ -156,6 +156,11 @@ CONFIGS = [
     ("n8_indirect", 8, True, 2.0, 1.0, 0.001, "standard", 6, False),
     ("n12_direct", 12, False, 2.0, 1.0, 0.0, "standard", 6, False),
     ("n12_indirect_dense", 12, True, 1.3, 0.0, 0.01, "dense", 6, True),
+    # player counts at and above the warp-assist threshold (skyjo_step.cuh SKYJO_ASSIST_MIN_N = 6)
+    ("n6_direct", 6, False, 2.0, 1.0, 0.0, "standard", 8, False),
+    ("n6_direct_dense", 6, False, 2.5, 1.0, 0.02, "dense", 8, True),
+    ("n7_indirect_dense", 7, True, 1.5, 1.0, 0.01, "dense", 6, True),
+    ("n10_direct", 10, False, 2.0, 0.0, 0.0, "standard", 6, False),
 ]
 
 
