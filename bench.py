@@ -287,7 +287,7 @@ def run_ours(args, rank, local_rank, world):
     stats = env.stats(all_reduce=world > 1)   # statistics of the timed region
     counted_frac = counted / float(B * world * K)
 
-    # roofline of the dominant kernel: mean device time of the step kernel from per-launch events
+    # roofline of the dominant kernel: mean device time of a step launch (event pair per window of back-to-back launches)
     env.clear_stats()
     prof = env.step_random_profile(min(K, 512))
     step_us = 1e3 * prof["step_ms"] / max(prof["step_launches"], 1)

@@ -195,13 +195,16 @@ typedef struct SkyjoRollout {
  * episode" meaning (an episode that ends inside a launch is visible in the statistics, its
  * reward row is cleared by the env's next step as in skyjo_env.py:250-252). */
 int skyjo_rollout_random(SkyjoHandle *h, int n_steps, const SkyjoRollout *out, void *stream);
-/* Per-kernel CUDA-event timing of everything launched between begin and end on `stream`
- * (summed device ms and launch counts of step / rollout kernels and of deal kernels); end
- * synchronises.  Measurement aid for bench.py's roofline figure. */
+/* CUDA-event timing of everything launched between begin and end on `stream` (summed device ms
+ * and launch counts of step / rollout kernels and of deal kernels); end synchronises.  One event
+ * pair brackets each deal or rollout launch, and each WINDOW of back-to-back single-step launches
+ * (the up to 8 launches between two refill deals): an event between two ~45 us step kernels would
+ * add ~5 us to each pair and break their programmatic dependent launch.  Measurement aid for
+ * bench.py's roofline figure. */
 int skyjo_profile_begin(SkyjoHandle *h);
 int skyjo_profile_end(SkyjoHandle *h, void *stream, double *step_ms, double *deal_ms,
                       int64_t *n_step_launches, int64_t *n_deal_launches);
-/* skyjo_step_random with every kernel bracketed by CUDA events on `stream`: returns the summed
+/* skyjo_step_random on one stream between skyjo_profile_begin / _end: returns the summed
  * device time (ms) and launch counts of the step kernels and of the deal kernels; synchronises.
  * Measurement aid for bench.py's roofline figure. */
 int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double *step_ms,

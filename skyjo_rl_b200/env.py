@@ -224,7 +224,8 @@ class BatchedSkyjoEnv:
         return {"step_ms": sm.value, "deal_ms": dm.value, "step_launches": ns.value, "deal_launches": nd.value}
 
     def step_random_profile(self, n_steps):
-        """step_random with per-kernel CUDA-event timing; returns a dict of device times."""
+        """step_random on one stream with CUDA-event timing (one pair per window of back-to-back step launches,
+        one per refill deal); returns the summed device times and the launch counts."""
         sm, dm = C.c_double(0), C.c_double(0)
         ns, nd = C.c_int64(0), C.c_int64(0)
         _lib.check(self._L.skyjo_step_random_profile(self._h, int(n_steps), self._stream(), C.byref(sm),
