@@ -11,7 +11,7 @@ What is the reference's and what is ours:
     in-game reshuffles are INPUTS, injected as SURVEY.md 9.8 describes
     (SkyjoGame._reshuffle_discard_pile is monkey-patched with tests/rng_twin.reshuffle so the
     GPU can reproduce np.random.shuffle's role deterministically).
-gym / pettingzoo are not installed; empty stub modules are registered so that skyjo_env.py
+gym / pettingzoo are not installed; the stand-ins of tests/shims are put on the path so that skyjo_env.py
 imports -- none of their code is exercised by _calc_final_rewards.
 """
 import os
@@ -28,18 +28,11 @@ import rng_twin  # noqa: E402
 
 
 def _stub_modules():
-    gym = types.ModuleType("gym")
-    gym.spaces = types.ModuleType("gym.spaces")
-    pz = types.ModuleType("pettingzoo")
-
-    class AECEnv:  # only needed as a base class name
-        pass
-
-    pz.AECEnv = AECEnv
-    pz.utils = types.ModuleType("pettingzoo.utils")
-    pz.utils.wrappers = types.ModuleType("pettingzoo.utils.wrappers")
-    sys.modules.update({"gym": gym, "gym.spaces": gym.spaces, "pettingzoo": pz,
-                        "pettingzoo.utils": pz.utils, "pettingzoo.utils.wrappers": pz.utils.wrappers})
+    """gym / pettingzoo are not installed: put the stand-ins of tests/shims on the path (the same ones
+    tests/golden/make_env_trace.py runs the whole env on), unless the real packages are importable."""
+    import importlib.util
+    if importlib.util.find_spec("gym") is None or importlib.util.find_spec("pettingzoo") is None:
+        sys.path.insert(0, os.path.join(os.path.dirname(HERE), "shims"))
 
 
 _stub_modules()

@@ -212,3 +212,15 @@ def test_sample_run_driver_plays_the_requested_games():
     st = sample_run(games=300, config={"num_players": 2}, num_envs=256)
     assert st["episodes"] >= 300 and st["illegal"] == 0
     assert 60 < st["episode_steps"] / st["episodes"] < 95     # ~76 act() calls per 2-player game
+
+
+def test_gpu_aec_replays_reference_env_traces():
+    # whole episodes recorded from the unmodified SimpleSkyjoEnv under the wrapper stack of skyjo_env.env()
+    # (tests/golden/make_env_trace.py), half of them ended by an illegal action, through the CUDA env
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    from skyjo_rl_b200.aec import SkyjoAECView
+    from test_env_trace import load_env_traces, replay_config
+    iterations = 0
+    for name, c in load_env_traces():
+        iterations += replay_config(lambda kw: SkyjoAECView(BatchedSkyjoEnv(num_envs=1, auto_reset=False, **kw), 0), c)
+    assert iterations > 900
