@@ -105,3 +105,44 @@ def test_rllib_dict_view_protocol():
     exp = g.final_rewards(mr, rr)
     assert np.array([rew[f"player_{i}"] for i in range(N)]).tobytes() == exp.tobytes()
     assert set(obs) == {f"player_{i}" for i in range(N)}
+
+
+def config_sweep_288(make_backend):
+    # the reference's own env test (tests/environment/test_skyjo_env_nojit.py:11-48) plays one simple_episode for each
+    # of num_players 1..12 x score_penalty {1,2} x indirect {T,F} x mean_reward {-1,0,1} x reward_refunded {0,0.01};
+    # here every one of the 288 episodes is also compared with the oracle, observation by observation
+    from itertools import product
+    rng = np.random.default_rng(11)
+    steps = 0
+    for count, (N, pen, indirect, mr, rr) in enumerate(product(range(1, 13), [1.0, 2.0], [True, False],
+                                                               [-1, 0.0, 1.0], [0.0, 0.01])):
+        seed, env_id = 1000 + count, count
+        be = make_backend(num_envs=1, num_players=N, score_penalty=pen, observe_other_player_indirect=indirect,
+                          mean_reward=mr, reward_refunded=rr, seed=seed, auto_reset=False, first_global_env_id=env_id)
+        aec = SkyjoAECView(be, 0)
+        aec.reset()
+        g = O.OracleGame(N, pen, indirect)
+        g.reset_rng(seed, env_id, 0)
+        finished = []
+        for agent in aec.agent_iter(max_iter=400 * N):
+            obs, reward, done, info = aec.last()
+            if done:
+                finished.append(reward)
+                aec.step(None)
+                continue
+            pid = g.expected_action[0]
+            o, m = g.collect_observation(pid)
+            assert agent == f"player_{pid}"
+            np.testing.assert_array_equal(obs["observations"], o)
+            np.testing.assert_array_equal(obs["action_mask"], m)
+            a = policy_ra(obs["observations"], obs["action_mask"], rng)
+            g.act(pid, a)
+            aec.step(a)
+            steps += 1
+        assert g.is_terminated and not aec.agents
+        assert np.array(finished).tobytes() == g.final_rewards(mr, rr).tobytes(), (N, pen, indirect, mr, rr)
+    assert count == 287 and steps > 288 * 20
+
+
+def test_reference_config_sweep_288_against_the_oracle():
+    config_sweep_288(_Backend)

@@ -224,3 +224,11 @@ def test_gpu_aec_replays_reference_env_traces():
     for name, c in load_env_traces():
         iterations += replay_config(lambda kw: SkyjoAECView(BatchedSkyjoEnv(num_envs=1, auto_reset=False, **kw), 0), c)
     assert iterations > 900
+
+
+def test_reference_config_sweep_288_against_the_oracle():
+    # reference tests/environment/test_skyjo_env_nojit.py:11-48 (288 configurations, one AEC episode each), every
+    # observation and the final rewards compared with the oracle
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    from test_aec_cpu import config_sweep_288
+    config_sweep_288(BatchedSkyjoEnv)
