@@ -512,13 +512,16 @@ def run_e2e(args, env, dev, rank, world):
     st = e.stats(all_reduce=world > 1)       # the timed steps only
     e.check()
     assert st["illegal"] == 0, "replayed actions must be legal"
-    # bytes that cross the link per step (csrc/skyjo_hostio.cuh): obs rows as they are, mask + agent + done as
-    # one packed word per env, a 4-byte count, and one {env, N rewards} entry per episode that ended
+    # bytes that cross the link per step (csrc/skyjo_hostio.cuh), as counted by the library from the copies it
+    # queues: one compact observation record (12 + 6 R + ceil(R / 2) bytes for a row of 19 + 12 R) and one packed
+    # mask + agent + done word per env, an 8-byte count; plus one {env, N rewards} entry (written by the pack kernel
+    # straight into host-mapped memory) per episode that ended
     ended_per_step = (st["episodes"] + st["truncated"]) / float(T * world)
-    d2h = B * (D + 4) + 4 + int(ended_per_step * (8 + 8 * N))
+    d2h = e.host_wire_bytes + int(ended_per_step * (8 + 8 * N))
     return {"value": st["steps"] / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": B,
             "d2h_bytes_per_step": d2h, "steps": T,
             "host_buffer_bytes_filled_per_step": B * (D + 26 + 1 + 1 + 8 * N),
+            "wire_bytes_per_env": round(e.host_wire_bytes / float(B), 2),
             "api": "skyjo_step_host (C ABI) via BatchedSkyjoEnv.step_host, pinned host buffers: obs int8[B,D], "
                    "mask int8[B,26], agent, done, reward f64[B,N] all filled every step"}
 

@@ -216,14 +216,24 @@ int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double 
  * buffers are complete (the refill deal of finished envs may still be running on `stream`).
  * Wire format (csrc/skyjo_hostio.cuh): mask + agent + done cross the link as one 32-bit word per
  * env and are expanded on the host by a few worker threads; reward rows cross only for envs
- * whose episode ended in this step, the other rows are zero-filled on the host.  Use pinned
- * host buffers for full link speed, and the same reward buffer on consecutive calls. */
+ * whose episode ended in this step, the other rows are zero-filled on the host; observation
+ * rows are copied as they are (or as compact records, skyjo_set_host_wire).  Use pinned host
+ * buffers for full link speed, and the same reward buffer on consecutive calls. */
 int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host,
                     int8_t *mask_host, int8_t *agent_host, uint8_t *done_host,
                     double *reward_host, void *stream);
 /* worker threads skyjo_step_host uses for the host-side expansion; 0 = default
  * (min(4, hardware threads / LOCAL_WORLD_SIZE), or SKYJO_HOST_THREADS) */
 int skyjo_set_host_threads(SkyjoHandle *h, int n);
+/* how observation rows cross the link in skyjo_step_host: 0 (default) = as they are, straight
+ * into obs_host by the copy engine; 1 = compact records of 12 + 6 R + ceil(R / 2) bytes for a
+ * row of 19 + 12 R bytes, packed on the device and expanded on the host by the worker threads
+ * (env SKYJO_HOST_WIRE=compact selects 1 at creation).  Mode 1 moves 1.7x fewer bytes but pays
+ * for it in host memory traffic: it only wins where the link, not the host, is the bottleneck
+ * (on the B200 box of this round, 16 host threads: 5.4e8 vs 7.3e8 env-steps/s -- DESIGN.md). */
+int skyjo_set_host_wire(SkyjoHandle *h, int mode);
+/* bytes the last skyjo_step_host call moved device -> host */
+int64_t skyjo_host_wire_bytes(const SkyjoHandle *h);
 
 /* SimpleSkyjoEnv.observe(agent) (skyjo_env.py:199-214) for an arbitrary seat; agent = -1
  * means each env's agent_selection.  Writes int8[B,D] / int8[B,26]. */
@@ -272,6 +282,13 @@ int skyjo_host_policy(uint64_t seed, uint64_t global_env, uint64_t t, uint32_t l
  * (null outputs are skipped). */
 void skyjo_host_expand_packed(const uint32_t *packed, int64_t n, int8_t *mask, int8_t *agent,
                               uint8_t *done);
+/* The compact observation record of skyjo_step_host (csrc/skyjo_hostio.cuh): bytes per record for
+ * rows of obs_len bytes (-1 if obs_len is not 19 + 12 R); the host twin of the device-side
+ * packing (returns the number of rows that are not encodable); and the host-side expansion
+ * (portable != 0 forces the scalar version instead of the 16-byte shuffles). */
+int skyjo_host_obs_record_bytes(int obs_len);
+int64_t skyjo_host_pack_obs(const int8_t *obs, int64_t n, int obs_len, uint8_t *rec);
+void skyjo_host_expand_obs(const uint8_t *rec, int64_t n, int obs_len, int8_t *obs, int portable);
 
 #ifdef __cplusplus
 }

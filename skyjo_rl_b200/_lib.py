@@ -33,7 +33,8 @@ EXPORTS = [
     "skyjo_step_random_profile", "skyjo_step_host", "skyjo_set_host_threads", "skyjo_observe", "skyjo_stats_device",
     "skyjo_stats_host", "skyjo_stats_clear", "skyjo_sample_actions", "skyjo_quiesce", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
     "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
-    "skyjo_host_policy", "skyjo_host_expand_packed",
+    "skyjo_host_policy", "skyjo_host_expand_packed", "skyjo_set_host_wire", "skyjo_host_wire_bytes",
+    "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs",
 ]
 
 
@@ -124,6 +125,8 @@ def load():
                                              C.POINTER(i64), C.POINTER(i64)]),
         "skyjo_step_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "skyjo_set_host_threads": (i32, [vp, i32]),
+        "skyjo_set_host_wire": (i32, [vp, i32]),
+        "skyjo_host_wire_bytes": (i64, [vp]),
         "skyjo_observe": (i32, [vp, i32, vp, vp, vp]),
         "skyjo_stats_device": (i32, [vp, vp, vp]),
         "skyjo_stats_host": (i32, [vp, vp, vp]),
@@ -140,6 +143,9 @@ def load():
         "skyjo_host_flips": (None, [u64, u64, u32, i32, vp]),
         "skyjo_host_policy": (i32, [u64, u64, u64, u32]),
         "skyjo_host_expand_packed": (None, [vp, i64, vp, vp, vp]),
+        "skyjo_host_obs_record_bytes": (i32, [i32]),
+        "skyjo_host_pack_obs": (i64, [vp, i64, i32, vp]),
+        "skyjo_host_expand_obs": (None, [vp, i64, i32, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -97,7 +97,11 @@ struct SkyjoHandle {
     cudaStream_t copy_stream;
     cudaEvent_t ev_chunk_ready[HOSTIO_MAX_CHUNKS], ev_small_done[HOSTIO_MAX_CHUNKS], ev_counter_done, ev_all_done;
     uint32_t *packed_dev, *packed_host;     // [B]
-    unsigned int *counter_dev, *counter_host;
+    unsigned int *counter_dev, *counter_host;   // [2]: finished envs of the call, "row not encodable" flag
+    uint8_t *rec_dev, *rec_host;            // compact observation records, [B][obs_record_bytes(D)]
+    cudaEvent_t ev_rec_done[HOSTIO_MAX_CHUNKS];
+    int wire_mode;                          // 0 raw rows (default), 1 compact records
+    long long last_d2h_bytes;               // bytes queued device -> host by the last skyjo_step_host
     double *entries_host, *entries_dev;     // host-mapped pinned, [cap][1 + N]
     unsigned int sparse_cap;
     int host_threads;
@@ -248,6 +252,10 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     h->hostio_ready = false;
     h->pool = nullptr;
     h->host_threads = 0;
+    h->wire_mode = 0;
+    if (const char *g = getenv("SKYJO_HOST_WIRE")) h->wire_mode = (atoi(g) == 1 || !strcmp(g, "compact")) ? 1 : 0;
+    h->last_d2h_bytes = 0;
+    h->rec_dev = h->rec_host = nullptr;
     h->last_reward_host = nullptr;
     h->trace_calls = 0;
     for (double &v : h->trace_us) v = 0.0;
@@ -279,9 +287,12 @@ static void hostio_release(SkyjoHandle *h) {
     cudaFreeHost(h->packed_host);
     cudaFreeHost(h->counter_host);
     cudaFreeHost(h->entries_host);
+    cudaFree(h->rec_dev);
+    cudaFreeHost(h->rec_host);
     for (int c = 0; c < HOSTIO_MAX_CHUNKS; ++c) {
         cudaEventDestroy(h->ev_chunk_ready[c]);
         cudaEventDestroy(h->ev_small_done[c]);
+        cudaEventDestroy(h->ev_rec_done[c]);
     }
     cudaEventDestroy(h->ev_counter_done);
     cudaEventDestroy(h->ev_all_done);
@@ -713,13 +724,16 @@ static int hostio_init(SkyjoHandle *h) {
     for (int c = 0; c < HOSTIO_MAX_CHUNKS; ++c) {
         CU(cudaEventCreateWithFlags(&h->ev_chunk_ready[c], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_small_done[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_rec_done[c], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&h->ev_counter_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_all_done, cudaEventDisableTiming));
     CU(cudaMalloc(&h->packed_dev, B * 4));
-    CU(cudaMalloc(&h->counter_dev, 4));
+    CU(cudaMalloc(&h->counter_dev, 8));
     CU(cudaHostAlloc(&h->packed_host, B * 4, cudaHostAllocDefault));
-    CU(cudaHostAlloc(&h->counter_host, 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&h->counter_host, 8, cudaHostAllocDefault));
+    CU(cudaMalloc(&h->rec_dev, B * (size_t)obs_record_bytes(h->obs_len)));
+    CU(cudaHostAlloc(&h->rec_host, B * (size_t)obs_record_bytes(h->obs_len), cudaHostAllocDefault));
     CU(cudaHostAlloc(&h->entries_host, (size_t)h->sparse_cap * (1 + N) * 8, cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer(&h->entries_dev, h->entries_host, 0));
     h->hostio_ready = true;
@@ -749,9 +763,11 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     rc = quiesce(h, s);
     if (rc) return rc;
     const bool want_small = mask_host || agent_host || done_host || reward_host;
-    if (want_small) CU(cudaMemsetAsync(h->counter_dev, 0, 4, s));
+    const bool compact = obs_host && h->wire_mode == 1;
+    const int RB = obs_record_bytes(h->obs_len);
+    if (want_small || compact) CU(cudaMemsetAsync(h->counter_dev, 0, 8, s));
     // env ranges: multiples of ENV_PAD envs, so every range starts on a tile and on a 16-byte boundary
-    int chunks = h->B >= (1 << 18) ? 4 : (h->B >= (1 << 16) ? 2 : 1);
+    int chunks = h->B >= (1 << 18) ? (compact ? 8 : 4) : (h->B >= (1 << 16) ? 2 : 1);
     if (const char *g = getenv("SKYJO_HOST_CHUNKS")) chunks = atoi(g);
     if (chunks < 1) chunks = 1;
     if (chunks > HOSTIO_MAX_CHUNKS) chunks = HOSTIO_MAX_CHUNKS;
@@ -766,6 +782,7 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     StepParams p = make_params(h);
     p.actions = act_dev;
     p.action_dtype = SKYJO_ACT_U8;
+    long long d2h = 0;
     for (int c = 0; c < nc; ++c) {
         const size_t e0 = (size_t)c_begin[c], n = (size_t)(c_end[c] - c_begin[c]);
         CU(cudaMemcpyAsync(act_dev + e0, actions_host + e0, n, cudaMemcpyHostToDevice, s));
@@ -781,20 +798,35 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
             h->launches += 1;
             CU(cudaGetLastError());
         }
+        if (compact) {
+            compact_obs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+                (const int8_t *)h->outs.obs_dev, c_begin[c], c_end[c], h->obs_len, RB, h->rec_dev, h->counter_dev + 1);
+            h->launches += 1;
+            CU(cudaGetLastError());
+        }
         CU(cudaEventRecord(h->ev_chunk_ready[c], s));
         CU(cudaStreamWaitEvent(cs, h->ev_chunk_ready[c], 0));
         if (want_small) {
             CU(cudaMemcpyAsync(h->packed_host + e0, h->packed_dev + e0, n * 4, cudaMemcpyDeviceToHost, cs));
             CU(cudaEventRecord(h->ev_small_done[c], cs));
+            d2h += (long long)n * 4;
         }
-        if (obs_host)
+        if (compact) {
+            CU(cudaMemcpyAsync(h->rec_host + e0 * (size_t)RB, h->rec_dev + e0 * (size_t)RB, n * (size_t)RB,
+                               cudaMemcpyDeviceToHost, cs));
+            CU(cudaEventRecord(h->ev_rec_done[c], cs));
+            d2h += (long long)n * RB;
+        } else if (obs_host) {
             CU(cudaMemcpyAsync(obs_host + e0 * (size_t)h->obs_len, (const int8_t *)h->outs.obs_dev + e0 * (size_t)h->obs_len,
                                n * (size_t)h->obs_len, cudaMemcpyDeviceToHost, cs));
+            d2h += (long long)n * h->obs_len;
+        }
     }
     h->t += 1;
-    if (reward_host) {
-        CU(cudaMemcpyAsync(h->counter_host, h->counter_dev, 4, cudaMemcpyDeviceToHost, cs));
+    if (reward_host || compact) {
+        CU(cudaMemcpyAsync(h->counter_host, h->counter_dev, 8, cudaMemcpyDeviceToHost, cs));
         CU(cudaEventRecord(h->ev_counter_done, cs));
+        d2h += 8;
     }
     CU(cudaEventRecord(h->ev_all_done, cs));
     // external actions may end any episode at once: refill after every step (queued behind the last
@@ -804,31 +836,35 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     if (rc) return rc;
     lap(0);
 
-    if (want_small) {
-        // previous call's reward rows back to zero while the first packed words travel
-        if (reward_host) {
-            if (h->last_reward_host != reward_host) {
-                memset(reward_host, 0, B * N * 8);
-                h->last_reward_host = reward_host;
-            } else {
-                for (long long e : h->last_reward_rows) memset(reward_host + (size_t)e * N, 0, N * 8);
-            }
-            h->last_reward_rows.clear();
+    // previous call's reward rows back to zero while the first chunk travels
+    if (reward_host) {
+        if (h->last_reward_host != reward_host) {
+            memset(reward_host, 0, B * N * 8);
+            h->last_reward_host = reward_host;
+        } else {
+            for (long long e : h->last_reward_rows) memset(reward_host + (size_t)e * N, 0, N * 8);
         }
+        h->last_reward_rows.clear();
+    }
+    if (want_small || compact) {
         const uint32_t *packed = h->packed_host;
+        const uint8_t *rec = h->rec_host;
+        const int D = h->obs_len;
         for (int c = 0; c < nc; ++c) {
-            CU(cudaEventSynchronize(h->ev_small_done[c]));
+            // the record copy of a chunk is queued behind its packed words: one wait covers both
+            CU(cudaEventSynchronize(compact ? h->ev_rec_done[c] : h->ev_small_done[c]));
             lap(1);
             const long long b0 = c_begin[c], nB = c_end[c] - c_begin[c];
             h->pool->run([=](int part, int parts) {
                 const long long e0 = b0 + nB * part / parts, e1 = b0 + nB * (part + 1) / parts;
-                expand_packed(packed, e0, e1, mask_host, agent_host, done_host);
+                if (want_small) expand_packed(packed, e0, e1, mask_host, agent_host, done_host);
+                if (compact) expand_obs_records(rec, e0, e1, D, obs_host);
             });
             lap(2);
         }
+        if (reward_host || compact) CU(cudaEventSynchronize(h->ev_counter_done));
         if (reward_host) {
-            CU(cudaEventSynchronize(h->ev_counter_done));
-            const unsigned int cnt = *h->counter_host;
+            const unsigned int cnt = h->counter_host[0];
             if (cnt <= h->sparse_cap) {
                 // every pack kernel finished before ev_counter_done: its writes to the mapped buffer are visible
                 for (unsigned int i = 0; i < cnt; ++i) {
@@ -841,16 +877,32 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
                 // more finished envs than the compact buffer holds: dense copy of the reward tensor
                 CU(cudaMemcpyAsync(reward_host, h->outs.reward_dev, B * N * 8, cudaMemcpyDeviceToHost, cs));
                 CU(cudaEventRecord(h->ev_all_done, cs));
+                d2h += (long long)(B * N * 8);
                 h->last_reward_host = nullptr;  // every row may be non-zero: start from a memset next time
             }
+        }
+        if (compact && h->counter_host[1] != 0u) {
+            // a row outside the record's symbol sets (not reachable from the 4-bit-bin state layout): dense copy
+            CU(cudaMemcpyAsync(obs_host, h->outs.obs_dev, B * (size_t)D, cudaMemcpyDeviceToHost, cs));
+            CU(cudaEventRecord(h->ev_all_done, cs));
+            d2h += (long long)(B * (size_t)D);
         }
     }
     lap(3);
     CU(cudaEventSynchronize(h->ev_all_done));
     lap(4);
     h->trace_calls += 1;
+    h->last_d2h_bytes = d2h;
     return SKYJO_OK;
 }
+
+int skyjo_set_host_wire(SkyjoHandle *h, int mode) {
+    if (!h || (mode != 0 && mode != 1)) return fail(SKYJO_E_INVALID, "wire mode must be 0 (raw rows) or 1 (compact records)");
+    h->wire_mode = mode;
+    return SKYJO_OK;
+}
+
+int64_t skyjo_host_wire_bytes(const SkyjoHandle *h) { return h ? h->last_d2h_bytes : -1; }
 
 int skyjo_observe(SkyjoHandle *h, int agent, void *obs_dev, void *mask_dev, void *stream) {
     if (!h || !obs_dev || !mask_dev) return fail(SKYJO_E_INVALID, "null argument");
@@ -993,6 +1045,22 @@ void skyjo_host_flips(uint64_t seed, uint64_t genv, uint32_t episode, int num_pl
 
 void skyjo_host_expand_packed(const uint32_t *packed, int64_t n, int8_t *mask, int8_t *agent, uint8_t *done) {
     expand_packed(packed, 0, n, mask, agent, done);
+}
+
+int skyjo_host_obs_record_bytes(int obs_len) { return obs_len >= 31 && (obs_len - 19) % 12 == 0 ? obs_record_bytes(obs_len) : -1; }
+
+int64_t skyjo_host_pack_obs(const int8_t *obs, int64_t n, int obs_len, uint8_t *rec) {
+    const int RB = obs_record_bytes(obs_len);
+    int64_t bad = 0;
+    for (int64_t e = 0; e < n; ++e) bad += pack_obs_record(obs + e * obs_len, obs_len, rec + e * RB) ? 0 : 1;
+    return bad;
+}
+
+void skyjo_host_expand_obs(const uint8_t *rec, int64_t n, int obs_len, int8_t *obs, int portable) {
+    if (portable)
+        expand_obs_scalar(rec, 0, n, obs_len, obs);
+    else
+        expand_obs_records(rec, 0, n, obs_len, obs);
 }
 
 int skyjo_host_policy(uint64_t seed, uint64_t genv, uint64_t t, uint32_t legal_bits) {

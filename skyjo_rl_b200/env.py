@@ -282,6 +282,16 @@ class BatchedSkyjoEnv:
         """Worker threads step_host uses to expand the packed mask / agent / done words (0 = default)."""
         _lib.check(self._L.skyjo_set_host_threads(self._h, int(n)))
 
+    def set_host_wire(self, mode="raw"):
+        """How step_host moves observation rows over the link: "raw" rows (default) or "compact" records, packed
+        on the device and expanded on the host (csrc/skyjo_hostio.cuh)."""
+        _lib.check(self._L.skyjo_set_host_wire(self._h, {"raw": 0, "compact": 1}[mode]))
+
+    @property
+    def host_wire_bytes(self):
+        """bytes the last step_host call moved device -> host"""
+        return int(self._L.skyjo_host_wire_bytes(self._h))
+
     def observe(self, agent=None):
         """SimpleSkyjoEnv.observe (skyjo_env.py:199-214).  agent=None returns the live buffers
         (view of each env's agent_selection); a name or index encodes that seat's view."""

@@ -232,3 +232,30 @@ def test_reference_config_sweep_288_against_the_oracle():
     from skyjo_rl_b200 import BatchedSkyjoEnv
     from test_aec_cpu import config_sweep_288
     config_sweep_288(BatchedSkyjoEnv)
+
+
+def test_integration_md_stub_plays_the_same_games_as_the_shipped_mirror():
+    # the reference-side ctypes stub documented in INTEGRATION.md, executed as written, against BatchedSkyjoEnv
+    import ctypes as C  # noqa: F401
+    from integration_stub import load_stub
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    m = load_stub()
+    cfg = {"num_players": 3, "score_penalty": 2.0, "observe_other_player_indirect": True, "mean_reward": 1.0,
+           "reward_refunded": 0.001}                                            # skyjo_env.DEFAULT_CONFIG
+    B = 4096
+    h, state, b = m.make(B, seed=5, **cfg)
+    env = BatchedSkyjoEnv(num_envs=B, seed=5, auto_reset=True, **cfg)
+    s = torch.cuda.current_stream().cuda_stream
+    assert m.L.skyjo_reset(h, s) == 0
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ended = 0
+    for t in range(300):
+        assert torch.equal(b["obs"], env.observations) and torch.equal(b["mask"], env.action_mask)
+        assert torch.equal(b["agent"], env.agent_selection)
+        a = torch.multinomial(b["mask"].float(), 1, generator=g).squeeze(1)     # int64, uniform over legal actions
+        assert m.L.skyjo_step(h, a.data_ptr(), 3, s) == 0                       # 3 = SKYJO_ACT_I64
+        env.step(a)
+        assert torch.equal(b["done"], env.done_code) and torch.equal(b["reward"], env.rewards)
+        ended += int((b["done"] != 0).sum())
+    assert ended > B

@@ -104,3 +104,87 @@ def test_host_expand_packed_matches_numpy_unpack():
     np.testing.assert_array_equal(agent, (packed >> 28).astype(np.int8))
     np.testing.assert_array_equal(done, ((packed >> 26) & 3).astype(np.uint8))
     L.skyjo_host_expand_packed(packed.ctypes.data, n, None, None, done.ctypes.data)   # null outputs are skipped
+
+
+def test_integration_md_stub_matches_the_binding():
+    # the reference-side ctypes stub documented in INTEGRATION.md loads the library and declares the same
+    # structures and signatures as the shipped binding (no compute call: there is no GPU here)
+    import ctypes as C
+    from integration_stub import load_stub
+    from skyjo_rl_b200 import _lib
+    m = load_stub()
+    for name in ("SkyjoConfig", "SkyjoOutputs"):
+        a, b = getattr(m, name), getattr(_lib, name)
+        assert C.sizeof(a) == C.sizeof(b)
+        assert [(f[0], f[1]) for f in a._fields_] == [(f[0], f[1]) for f in b._fields_]
+    L = _lib.load()
+    for fn in ("skyjo_state_bytes", "skyjo_create", "skyjo_bind_outputs", "skyjo_reset", "skyjo_step"):
+        got, exp = getattr(m.L, fn).argtypes, getattr(L, fn).argtypes
+        assert len(got) == len(exp) and all(C.sizeof(x) == C.sizeof(y) for x, y in zip(got, exp)), fn
+    cfg = m.SkyjoConfig(4, 0, 2.0, 1.0, 0.0, 1, 0)
+    assert m.L.skyjo_state_bytes(C.byref(cfg), 1 << 10) == L.skyjo_state_bytes(C.byref(_lib.SkyjoConfig(4, 0, 2.0, 1.0, 0.0, 1, 0)), 1 << 10)
+
+
+def _reference_observation_rows():
+    """every observation row the unmodified reference produced for the fixtures, grouped by row length"""
+    import os
+    from conftest import GOLDEN_DIR, golden_files
+    rows = {}
+    for f in golden_files():
+        z = np.load(os.path.join(GOLDEN_DIR, f))
+        for k in ("obs", "obs_other", "final_obs"):
+            a = z[k].astype(np.int8)
+            rows.setdefault(a.shape[1], []).append(a)
+    z = np.load(os.path.join(GOLDEN_DIR, "env_trace.npz"))
+    for k in z.files:
+        if k.endswith("/obs"):
+            rows.setdefault(z[k].shape[1], []).append(z[k].astype(np.int8))
+    return {D: np.ascontiguousarray(np.concatenate(v)) for D, v in rows.items()}
+
+
+def test_compact_observation_records_round_trip_on_every_reference_observation():
+    # wire format of skyjo_step_host (csrc/skyjo_hostio.cuh): expand(pack(row)) == row for every observation the
+    # reference produced in the fixtures (removed columns, dense decks, N = 1..12, both observation modes),
+    # through the 16-byte-shuffle expansion and through the portable one
+    from skyjo_rl_b200 import _lib
+    L = _lib.load()
+    total = removed = 0
+    for D, obs in sorted(_reference_observation_rows().items()):
+        R = (D - 19) // 12
+        RB = L.skyjo_host_obs_record_bytes(D)
+        assert RB == 12 + 6 * R + (R + 1) // 2 and RB < D
+        n = obs.shape[0]
+        rec = np.zeros((n, RB), dtype=np.uint8)
+        assert L.skyjo_host_pack_obs(obs.ctypes.data, n, D, rec.ctypes.data) == 0
+        for portable in (0, 1):
+            out = np.full((n + 1, D), 99, dtype=np.int8)           # one guard row behind the last one
+            L.skyjo_host_expand_obs(rec.ctypes.data, n, D, out.ctypes.data, portable)
+            np.testing.assert_array_equal(out[:n], obs)
+            assert (out[n] == 99).all()
+        total += n
+        removed += int((obs == -14).sum())
+    assert total > 20000 and removed > 3000          # the fixtures hold removed columns
+    assert L.skyjo_host_obs_record_bytes(67) == 38 and L.skyjo_host_obs_record_bytes(30) == -1
+
+
+def test_compact_observation_records_flag_rows_they_cannot_hold():
+    from skyjo_rl_b200 import _lib
+    L = _lib.load()
+    D = 67
+    good = np.zeros((1, D), dtype=np.int8)
+    good[0, 17] = -3
+    good[0, 18] = 15
+    good[0, 19:] = 15
+    rec = np.zeros((1, L.skyjo_host_obs_record_bytes(D)), dtype=np.uint8)
+    assert L.skyjo_host_pack_obs(good.ctypes.data, 1, D, rec.ctypes.data) == 0
+    for pos, val in ((19, 13), (25, -3), (2, 16), (5, -1), (17, 13), (18, 14), (1, 16), (40, -14)):
+        bad = good.copy()
+        bad[0, pos] = val           # a card / bin / top / hand outside the symbol sets, a lone -14
+        assert L.skyjo_host_pack_obs(bad.ctypes.data, 1, D, rec.ctypes.data) == 1, (pos, val)
+    ok = good.copy()
+    ok[0, 4] = 100                  # the value-0 bin travels as a whole byte
+    ok[0, 22:25] = -14              # a removed column
+    assert L.skyjo_host_pack_obs(ok.ctypes.data, 1, D, rec.ctypes.data) == 0
+    out = np.zeros_like(ok)
+    L.skyjo_host_expand_obs(rec.ctypes.data, 1, D, out.ctypes.data, 0)
+    np.testing.assert_array_equal(out, ok)
