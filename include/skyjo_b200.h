@@ -39,6 +39,7 @@ enum {
     SKYJO_E_NOT_BOUND = 2,  /* outputs not bound */
     SKYJO_E_STATE = 3,      /* device-side consistency flag raised (see skyjo_check) */
     SKYJO_E_NO_DEVICE = 4,
+    SKYJO_E_NCCL = 5,       /* ncclAllReduce returned an error (skyjo_stats_allreduce) */
     SKYJO_E_CUDA = 1000     /* + cudaError_t */
 };
 
@@ -244,6 +245,11 @@ int skyjo_observe(SkyjoHandle *h, int agent, void *obs_dev, void *mask_dev, void
  * copies to the host and synchronises. */
 int skyjo_stats_device(SkyjoHandle *h, int64_t *out_dev, void *stream);
 int skyjo_stats_host(SkyjoHandle *h, int64_t *out_host, void *stream);
+/* The library's only collective (never on the step path): skyjo_stats_device into out_dev followed
+ * by ncclAllReduce(sum, int64) over the ranks of `nccl_comm` (an ncclComm_t) on `stream`, in place.
+ * NCCL is resolved at run time from the libnccl already loaded in the process (torch's, or one the
+ * caller opened), never linked: fails with SKYJO_E_INVALID if there is none. */
+int skyjo_stats_allreduce(SkyjoHandle *h, void *nccl_comm, int64_t *out_dev, void *stream);
 int skyjo_stats_clear(SkyjoHandle *h, void *stream);
 
 /* Policy side of a rollout (BASELINE config 4): masked softmax + categorical sample of one action

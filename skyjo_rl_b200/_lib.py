@@ -34,7 +34,7 @@ EXPORTS = [
     "skyjo_stats_host", "skyjo_stats_clear", "skyjo_sample_actions", "skyjo_quiesce", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
     "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
     "skyjo_host_policy", "skyjo_host_expand_packed", "skyjo_set_host_wire", "skyjo_host_wire_bytes",
-    "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs",
+    "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs", "skyjo_stats_allreduce",
 ]
 
 
@@ -130,6 +130,7 @@ def load():
         "skyjo_observe": (i32, [vp, i32, vp, vp, vp]),
         "skyjo_stats_device": (i32, [vp, vp, vp]),
         "skyjo_stats_host": (i32, [vp, vp, vp]),
+        "skyjo_stats_allreduce": (i32, [vp, vp, vp, vp]),
         "skyjo_stats_clear": (i32, [vp, vp]),
         "skyjo_sample_actions": (i32, [vp, vp, vp, u64, vp, vp, vp, vp]),
         "skyjo_quiesce": (i32, [vp, vp]),

@@ -2,9 +2,9 @@
 // launch scheduling of the deal / step / observe kernels, statistics, host RNG twins.
 // No torch, no CPU fallback: every compute entry launches CUDA kernels or fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -922,6 +922,37 @@ int skyjo_stats_device(SkyjoHandle *h, int64_t *out_dev, void *stream) {
     stats_reduce_kernel<<<1, NUM_STATS, 0, (cudaStream_t)stream>>>(h->st.stats, (long long *)out_dev);
     h->launches += 1;
     CU(cudaGetLastError());
+    return SKYJO_OK;
+}
+
+// The one collective of the library: sum of the statistics vector over the ranks of an NCCL
+// communicator, off the step path.  NCCL is not a link-time dependency: the symbols are taken from whichever
+// libnccl the process has loaded (torch's bundled one under torch.distributed, or one the caller dlopen'ed with
+// RTLD_GLOBAL), so the communicator and the call always belong to the same NCCL build.
+int skyjo_stats_allreduce(SkyjoHandle *h, void *nccl_comm, int64_t *out_dev, void *stream) {
+    if (!h || !nccl_comm || !out_dev) return fail(SKYJO_E_INVALID, "null argument");
+    typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef const char *(*errstr_fn)(int);
+    static allreduce_fn all_reduce = nullptr;
+    static errstr_fn err_string = nullptr;
+    if (!all_reduce) {
+        all_reduce = (allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        err_string = (errstr_fn)dlsym(RTLD_DEFAULT, "ncclGetErrorString");
+        if (!all_reduce) {
+            if (void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD)) {  // loaded RTLD_LOCAL
+                all_reduce = (allreduce_fn)dlsym(lib, "ncclAllReduce");
+                err_string = (errstr_fn)dlsym(lib, "ncclGetErrorString");
+            }
+        }
+    }
+    if (!all_reduce) return fail(SKYJO_E_INVALID, "NCCL is not loaded in this process (ncclAllReduce not found)");
+    int rc = skyjo_stats_device(h, out_dev, stream);
+    if (rc) return rc;
+    const int ncclInt64 = 4, ncclSum = 0;  // nccl.h: ncclDataType_t / ncclRedOp_t
+    const int nrc = all_reduce(out_dev, out_dev, (size_t)NUM_STATS, ncclInt64, ncclSum, nccl_comm, (cudaStream_t)stream);
+    if (nrc != 0) {
+        return fail(SKYJO_E_NCCL, "ncclAllReduce failed: %s", err_string ? err_string(nrc) : "unknown NCCL error");
+    }
     return SKYJO_OK;
 }
 

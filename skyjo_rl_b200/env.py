@@ -337,10 +337,15 @@ class BatchedSkyjoEnv:
         _lib.check(self._L.skyjo_stats_device(self._h, out.data_ptr(), self._stream()))
         return out
 
-    def stats(self, all_reduce=False, group=None):
+    def stats(self, all_reduce=False, group=None, comm=None):
         """Episode statistics as a dict.  With all_reduce=True the vector is summed over the
         ranks of `group` with torch.distributed (NCCL) first -- the only collective of the env,
-        never on the step path."""
+        never on the step path.  With `comm` (a skyjo_rl_b200.nccl.StatsComm) the sum is the
+        library's own ncclAllReduce (skyjo_stats_allreduce) on the env's stream."""
+        if comm is not None:
+            vec = torch.empty(_lib.NUM_STATS, dtype=torch.int64, device=self.device)
+            _lib.check(self._L.skyjo_stats_allreduce(self._h, comm.handle, vec.data_ptr(), self._stream()))
+            return dict(zip(_lib.STAT_NAMES, vec.tolist()))
         vec = self.stats_tensor()
         if all_reduce:
             torch.distributed.all_reduce(vec, group=group)

@@ -259,3 +259,19 @@ def test_integration_md_stub_plays_the_same_games_as_the_shipped_mirror():
         assert torch.equal(b["done"], env.done_code) and torch.equal(b["reward"], env.rewards)
         ended += int((b["done"] != 0).sum())
     assert ended > B
+
+
+def test_in_library_nccl_stats_allreduce_single_rank():
+    # skyjo_stats_allreduce (the library's only collective) over a one-rank NCCL communicator created with the NCCL
+    # torch loaded: the sum over one rank is the rank's own vector; the multi-rank case is tools/gpu_nccl_stats.py
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    from skyjo_rl_b200.nccl import StatsComm
+    env = BatchedSkyjoEnv(num_envs=5000, num_players=4, seed=3)
+    env.reset()
+    env.step_random(300)
+    comm = StatsComm(env.device)
+    a = env.stats(comm=comm)
+    b = env.stats()
+    assert a == b and a["episodes"] > 5000 and a["steps"] > 0
+    comm.close()
+    env.check()
