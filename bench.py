@@ -240,6 +240,27 @@ def run_ours(args, rank, local_rank, world):
                           device=dev, seed=args.seed, first_global_env_id=rank * B, auto_reset=args.reset)
     env.reset()
     stats_vec = None
+    # the per-iteration statistics all-reduce (the only collective): the library's own ncclAllReduce on a
+    # communicator created with the NCCL torch loaded (skyjo_stats_allreduce); torch.distributed.all_reduce if that
+    # communicator cannot be created
+    comm = None
+    if world > 1:
+        try:
+            from skyjo_rl_b200.nccl import StatsComm
+            comm = StatsComm(dev)
+        except Exception as ex:  # noqa: BLE001
+            print(f"[bench] in-library NCCL communicator unavailable ({ex}); using torch.distributed", file=sys.stderr)
+        ok = torch.tensor([1 if comm is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            comm = None
+
+    def reduced_stats_tensor(e):
+        if comm is not None:
+            return e.stats_tensor(comm)
+        v = e.stats_tensor()
+        dist.all_reduce(v)
+        return v
 
     def counted_steps(allreduce=True):
         # act() transitions since the last clear_stats(), over all ranks
@@ -256,8 +277,7 @@ def run_ours(args, rank, local_rank, world):
             env.step_random(c)
             done += c
             if world > 1:
-                stats_vec = env.stats_tensor()
-                dist.all_reduce(stats_vec)
+                stats_vec = reduced_stats_tensor(env)
 
     def barrier():
         if world > 1:
@@ -285,6 +305,8 @@ def run_ours(args, rank, local_rank, world):
     counted = counted_steps()                 # == B * world * K in same_step mode
     value = counted / (ms * 1e-3)
     stats = env.stats(all_reduce=world > 1)   # statistics of the timed region
+    if comm is not None:                       # the in-library all-reduce against torch.distributed's
+        assert env.stats(comm=comm) == stats, "skyjo_stats_allreduce disagrees with torch.distributed.all_reduce"
     counted_frac = counted / float(B * world * K)
 
     # roofline of the dominant kernel: mean device time of a step launch (event pair per window of back-to-back launches)
@@ -332,7 +354,7 @@ def run_ours(args, rank, local_rank, world):
             for _ in range(reps):
                 env.rollout_random(T, ro)
                 if world > 1:
-                    dist.all_reduce(env.stats_tensor())
+                    reduced_stats_tensor(env)
             ev1.record()
             barrier()
             rms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
@@ -416,6 +438,8 @@ def run_ours(args, rank, local_rank, world):
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout,
             "counted_env_steps": counted, "counted_frac": counted_frac, "other_reset_mode": other,
             "policy_rollout": policy_rollout,
+            "stats_allreduce": None if world == 1 else ("skyjo_stats_allreduce (in-library ncclAllReduce, every 64 steps)"
+                                                        if comm is not None else "torch.distributed.all_reduce"),
             "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")},
         }
         print(json.dumps(line), flush=True)

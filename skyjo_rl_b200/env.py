@@ -331,10 +331,15 @@ class BatchedSkyjoEnv:
         return f"player_{int(index)}"
 
     # ---- statistics / debugging -------------------------------------------------------
-    def stats_tensor(self):
-        """int64[32] statistics vector on the device (input of the NCCL all-reduce)."""
+    def stats_tensor(self, comm=None):
+        """int64[32] statistics vector on the device (input of the NCCL all-reduce); with `comm` (a
+        skyjo_rl_b200.nccl.StatsComm) already summed over its ranks by the library's own ncclAllReduce
+        (skyjo_stats_allreduce), asynchronously on the env's stream."""
         out = torch.empty(_lib.NUM_STATS, dtype=torch.int64, device=self.device)
-        _lib.check(self._L.skyjo_stats_device(self._h, out.data_ptr(), self._stream()))
+        if comm is not None:
+            _lib.check(self._L.skyjo_stats_allreduce(self._h, comm.handle, out.data_ptr(), self._stream()))
+        else:
+            _lib.check(self._L.skyjo_stats_device(self._h, out.data_ptr(), self._stream()))
         return out
 
     def stats(self, all_reduce=False, group=None, comm=None):
@@ -343,9 +348,7 @@ class BatchedSkyjoEnv:
         never on the step path.  With `comm` (a skyjo_rl_b200.nccl.StatsComm) the sum is the
         library's own ncclAllReduce (skyjo_stats_allreduce) on the env's stream."""
         if comm is not None:
-            vec = torch.empty(_lib.NUM_STATS, dtype=torch.int64, device=self.device)
-            _lib.check(self._L.skyjo_stats_allreduce(self._h, comm.handle, vec.data_ptr(), self._stream()))
-            return dict(zip(_lib.STAT_NAMES, vec.tolist()))
+            return dict(zip(_lib.STAT_NAMES, self.stats_tensor(comm).tolist()))
         vec = self.stats_tensor()
         if all_reduce:
             torch.distributed.all_reduce(vec, group=group)
