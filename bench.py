@@ -196,7 +196,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -433,7 +433,7 @@ def run_ours(args, rank, local_rank, world):
                 cpu["python_reference_1core"] = pr
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "int8", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout,
             "counted_env_steps": counted, "counted_frac": counted_frac, "other_reset_mode": other,
@@ -572,7 +572,13 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="CPU-seconds of oracle work (baseline sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--python-reference", action="store_true")
+    ap.add_argument("--global-envs", type=int, default=0,
+                    help="strong scaling (SURVEY 8d C5): total envs fixed, split evenly over the GPUs (overrides --envs)")
     args = ap.parse_args()
+    args.scaling = "weak"
+    if args.global_envs > 0:
+        args.envs = args.global_envs // max(int(os.environ.get("WORLD_SIZE", 1)), 1)
+        args.scaling = "strong"
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
