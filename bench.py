@@ -467,28 +467,34 @@ def run_policy_rollout(args, dev):
     ptr = (env.observations.data_ptr(), env.action_mask.data_ptr())
     obs = {"observations": env.observations, "action_mask": env.action_mask}
 
-    def steps(n):
-        with torch.no_grad():
+    def steps(n, autocast):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
             for _ in range(n):
-                act, _ = env.sample_actions(policy(obs))
+                act, _ = env.sample_actions(policy(obs).float())
                 env.step(act)
 
-    steps(8)
-    env.clear_stats()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
-    ev0.record()
-    steps(T)
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    ms = ev0.elapsed_time(ev1)
-    st = env.stats()
+    def timed(autocast):
+        steps(8, autocast)
+        env.clear_stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        steps(T, autocast)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        ms = ev0.elapsed_time(ev1)
+        st = env.stats()
+        assert st["illegal"] == 0
+        return st["steps"] / (ms * 1e-3), ms / T
+
+    value, ms_per_step = timed(False)          # fp32, the reference's precision (RLlib TorchFC)
+    value_bf16, ms_bf16 = timed(True)          # the same policy under bf16 autocast (library tensor-core GEMMs)
     env.check()
     assert ptr == (env.observations.data_ptr(), env.action_mask.data_ptr()), "obs / mask must be consumed in place"
-    assert st["illegal"] == 0
     env.close()
-    return {"value": st["steps"] / (ms * 1e-3), "unit": UNIT, "envs": B, "steps": T, "ms_per_step": ms / T,
+    return {"value": value, "unit": UNIT, "envs": B, "steps": T, "ms_per_step": ms_per_step,
             "policy": "ActionMaskPolicy 2x256 tanh + value branch, fp32 (ATen GEMMs), fused masked-softmax-sample kernel",
+            "bf16_autocast": {"value": value_bf16, "ms_per_step": ms_bf16},
             "zero_copy": True, "reset": "same_step"}
 
 
