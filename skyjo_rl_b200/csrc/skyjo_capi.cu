@@ -289,6 +289,7 @@ static void hostio_release(SkyjoHandle *h) {
     cudaFreeHost(h->entries_host);
     cudaFree(h->rec_dev);
     cudaFreeHost(h->rec_host);
+    h->rec_dev = h->rec_host = nullptr;
     for (int c = 0; c < HOSTIO_MAX_CHUNKS; ++c) {
         cudaEventDestroy(h->ev_chunk_ready[c]);
         cudaEventDestroy(h->ev_small_done[c]);
@@ -732,8 +733,6 @@ static int hostio_init(SkyjoHandle *h) {
     CU(cudaMalloc(&h->counter_dev, 8));
     CU(cudaHostAlloc(&h->packed_host, B * 4, cudaHostAllocDefault));
     CU(cudaHostAlloc(&h->counter_host, 8, cudaHostAllocDefault));
-    CU(cudaMalloc(&h->rec_dev, B * (size_t)obs_record_bytes(h->obs_len)));
-    CU(cudaHostAlloc(&h->rec_host, B * (size_t)obs_record_bytes(h->obs_len), cudaHostAllocDefault));
     CU(cudaHostAlloc(&h->entries_host, (size_t)h->sparse_cap * (1 + N) * 8, cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer(&h->entries_dev, h->entries_host, 0));
     h->hostio_ready = true;
@@ -765,6 +764,10 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     const bool want_small = mask_host || agent_host || done_host || reward_host;
     const bool compact = obs_host && h->wire_mode == 1;
     const int RB = obs_record_bytes(h->obs_len);
+    if (compact && !h->rec_dev) {  // record staging of the opt-in wire mode, on its first use
+        CU(cudaMalloc(&h->rec_dev, B * (size_t)RB));
+        CU(cudaHostAlloc(&h->rec_host, B * (size_t)RB, cudaHostAllocDefault));
+    }
     if (want_small || compact) CU(cudaMemsetAsync(h->counter_dev, 0, 8, s));
     // env ranges: multiples of ENV_PAD envs, so every range starts on a tile and on a 16-byte boundary
     int chunks = h->B >= (1 << 18) ? (compact ? 8 : 4) : (h->B >= (1 << 16) ? 2 : 1);
