@@ -39,7 +39,10 @@ _stub_modules()
 from rlskyjo.environment.skyjo_env import SimpleSkyjoEnv  # noqa: E402
 from rlskyjo.game.skyjo import SkyjoGame  # noqa: E402
 
-_RESHUFFLE = {"ctx": None}
+# one context shared by every copy of this module a test session loads (the hook below is installed on the class, so
+# the copy that patched last must see the context whichever copy sets it)
+_RESHUFFLE = getattr(SkyjoGame, "_b200_reshuffle_ctx", None) or {"ctx": None}
+SkyjoGame._b200_reshuffle_ctx = _RESHUFFLE
 _orig_reshuffle = SkyjoGame._reshuffle_discard_pile
 
 
