@@ -36,6 +36,18 @@ class SkyjoAECView:
         self.agent_selection = None
         self._has_reset = False
         self._skip_agent_selection = None
+        # One-env backends with a host entry (BatchedSkyjoEnv.step_host -> skyjo_step_host) step through it: one
+        # library call returns the next agent's observation, mask, agent, done code and rewards in pinned host
+        # buffers, instead of a launch plus five small device-to-host copies; last() then reads the cached copy.
+        self._host = None
+        self._cached = None                  # (agent name, observations, action_mask) as published by the last step
+        if batched_env.num_envs == 1 and hasattr(batched_env, "step_host"):
+            import torch
+            pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731
+            self._host = {"act": pin((1,), torch.uint8), "obs": pin((1, batched_env.obs_len), torch.int8),
+                          "mask": pin((1, _lib.NUM_ACTIONS), torch.int8), "agent": pin((1,), torch.int8),
+                          "done": pin((1,), torch.uint8), "reward": pin((1, N), torch.float64)}
+            self._host_np = {k: v.numpy() for k, v in self._host.items()}
 
     # ---- spaces (delegated) ---------------------------------------------------------------
     def observation_space(self, agent):
@@ -52,6 +64,7 @@ class SkyjoAECView:
     def reset(self):
         """skyjo_env.py:254-267"""
         self.env.reset()
+        self._cached = None
         self.agents = self.possible_agents[:]
         self.rewards = {a: 0 for a in self.agents}
         self._cumulative_rewards = {a: 0 for a in self.agents}
@@ -74,6 +87,7 @@ class SkyjoAECView:
         self._begin_episode()
 
     def _begin_episode(self):
+        self._cached = None
         self.agents = self.possible_agents[:]
         self.rewards = {a: 0 for a in self.agents}
         self._cumulative_rewards = {a: 0 for a in self.agents}
@@ -89,6 +103,8 @@ class SkyjoAECView:
     def observe(self, agent):
         """skyjo_env.py:199-214: observation dict of any named agent"""
         assert self._has_reset, "reset() needs to be called before observe"  # OrderEnforcingWrapper
+        if self._cached is not None and self._cached[0] == agent:
+            return {"observations": self._cached[1].copy(), "action_mask": self._cached[2].copy()}
         o = self.env.observe(int(agent.split("_")[-1]))
         return {"observations": _np(o["observations"])[self.index].copy(),
                 "action_mask": _np(o["action_mask"])[self.index].copy()}
@@ -112,14 +128,23 @@ class SkyjoAECView:
             return self._was_done_step(action)
         assert action is not None and 0 <= int(action) < _lib.NUM_ACTIONS, \
             "action is not in action space"                     # AssertOutOfBoundsWrapper
-        # the batch steps in lockstep: every other env of the backend plays its first legal action
-        actions = np.argmax(_np(self.env.action_mask), axis=1).astype(np.uint8)
-        actions[self.index] = int(action)
-        self.env.step(actions)
-        code = int(_np(self.env.done_code)[self.index])
-        self.agent_selection = self._expected_agent()
+        if self._host is not None:
+            h, hn = self._host, self._host_np
+            hn["act"][0] = int(action)
+            self.env.step_host(h["act"], h["obs"], h["mask"], h["agent"], h["done"], h["reward"])
+            code = int(hn["done"][0])
+            self.agent_selection = f"player_{int(hn['agent'][0])}"
+            self._cached = (self.agent_selection, hn["obs"][0].copy(), hn["mask"][0].copy())
+            rw = hn["reward"][0]
+        else:
+            # the batch steps in lockstep: every other env of the backend plays its first legal action
+            actions = np.argmax(_np(self.env.action_mask), axis=1).astype(np.uint8)
+            actions[self.index] = int(action)
+            self.env.step(actions)
+            code = int(_np(self.env.done_code)[self.index])
+            self.agent_selection = self._expected_agent()
+            rw = _np(self.env.rewards)[self.index] if code != _lib.RUNNING else None
         if code != _lib.RUNNING:
-            rw = _np(self.env.rewards)[self.index]
             if code == _lib.DONE_ILLEGAL:
                 self._cumulative_rewards[agent] = 0              # TerminateIllegalWrapper
             self.rewards = {a: float(rw[int(a.split("_")[-1])]) for a in self.agents}
