@@ -427,7 +427,9 @@ def run_ours(args, rank, local_rank, world):
             s, dt = cpu_rollout(N, args.indirect, games, threads)
             cpu = {"value": s / dt, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{games} full games per thread x {threads} threads ({s} env-steps), C oracle port of "
-                             "sample_game.py:10-21 with the same Philox deal and uniform legal policy"}
+                             "sample_game.py:10-21 with the same Philox deal and uniform legal policy",
+                   "note": "the Python reference itself (numba JIT, cannot travel to this box) ran 2.0-2.3e4 env-steps/s "
+                           "per core in the build container: profiles/r1_v7_python_reference_container.txt"}
             pr = python_reference_rate(N) if args.python_reference else None
             if pr:
                 cpu["python_reference_1core"] = pr
