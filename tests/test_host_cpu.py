@@ -188,3 +188,30 @@ def test_compact_observation_records_flag_rows_they_cannot_hold():
     out = np.zeros_like(ok)
     L.skyjo_host_expand_obs(rec.ctypes.data, 1, D, out.ctypes.data, 0)
     np.testing.assert_array_equal(out, ok)
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 7, 8, 12])
+def test_compact_observation_records_round_trip_on_random_rows(R):
+    # every row length 19 + 12 R (R = 1 is also the indirect mode's row), random symbols from the sets a row can hold
+    from skyjo_rl_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(R)
+    D, n = 19 + 12 * R, 3001
+    obs = np.zeros((n, D), dtype=np.int8)
+    obs[:, 0] = rng.integers(-24, 128, n)
+    obs[:, 1] = rng.integers(0, 13, n)
+    obs[:, 2:17] = rng.integers(0, 16, (n, 15))
+    obs[:, 4] = rng.integers(0, 128, n)                      # the value-0 bin is a whole byte
+    obs[:, 17] = rng.integers(-3, 13, n)
+    obs[:, 18] = rng.choice(np.r_[np.arange(-2, 13), 15], n)
+    cards = rng.choice(np.r_[np.arange(-2, 13), 15, 15, 15], (n, R, 4, 3)).astype(np.int8)
+    cards[rng.random((n, R, 4)) < 0.15] = -14                # removed columns
+    obs[:, 19:] = cards.reshape(n, 12 * R)
+    RB = L.skyjo_host_obs_record_bytes(D)
+    rec = np.zeros((n, RB), dtype=np.uint8)
+    assert L.skyjo_host_pack_obs(obs.ctypes.data, n, D, rec.ctypes.data) == 0
+    for portable in (0, 1):
+        out = np.full((n + 1, D), 77, dtype=np.int8)
+        L.skyjo_host_expand_obs(rec.ctypes.data, n, D, out.ctypes.data, portable)
+        np.testing.assert_array_equal(out[:n], obs)
+        assert (out[n] == 77).all()
