@@ -33,6 +33,8 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--resume", default=None)
+    ap.add_argument("--tf32", action="store_true",
+                    help="let the learner's fp32 GEMMs (ATen) use TF32 tensor cores; the env path is integer and unaffected")
     a = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -40,6 +42,9 @@ def main(argv=None):
     dev = torch.device("cuda", local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
+    if a.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
     torch.manual_seed(a.seed)                      # identical initial weights on every rank
     cfg = dict(DEFAULT_CONFIG, num_players=a.players, observe_other_player_indirect=not a.direct)
     env = BatchedSkyjoEnv(num_envs=a.envs, device=dev, seed=a.seed, first_global_env_id=rank * a.envs, **cfg)
