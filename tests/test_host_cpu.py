@@ -215,3 +215,25 @@ def test_compact_observation_records_round_trip_on_random_rows(R):
         L.skyjo_host_expand_obs(rec.ctypes.data, n, D, out.ctypes.data, portable)
         np.testing.assert_array_equal(out[:n], obs)
         assert (out[n] == 77).all()
+
+
+def test_empty_and_invalid_inputs_are_errors_not_crashes():
+    # an empty batch, a null config, zero-length host helpers: error codes / no-ops, never a crash (no GPU needed:
+    # these are rejected before the device is touched)
+    L = _lib.load()
+    cfg = _lib.SkyjoConfig(4, 0, 2.0, 1.0, 0.0, 1, 0)
+    h = C.c_void_p()
+    assert L.skyjo_state_bytes(C.byref(cfg), 0) == -1
+    assert L.skyjo_create(C.byref(cfg), 0, 0, 0, 0, None, 0, C.byref(h)) == 1 and b"num_envs" in L.skyjo_last_error()
+    assert L.skyjo_create(C.byref(cfg), 0, 8, 0, -5, None, 0, C.byref(h)) == 1
+    assert L.skyjo_create(None, 0, 8, 0, 0, None, 0, C.byref(h)) == 1
+    bad = _lib.SkyjoConfig(4, 0, 2.0, 1.0, 0.0, 7, 0)                       # auto_reset outside SKYJO_RESET_*
+    assert L.skyjo_create(C.byref(bad), 0, 8, 0, 0, None, 0, C.byref(h)) == 1
+    assert L.skyjo_step(None, None, 0, None) != 0 and L.skyjo_reset(None, None) != 0
+    assert L.skyjo_stats_allreduce(None, None, None, None) == 1
+    assert L.skyjo_host_wire_bytes(None) == -1 and L.skyjo_set_host_wire(None, 0) == 1
+    assert L.skyjo_host_pack_obs(None, 0, 67, None) == 0                    # zero rows: nothing touched
+    L.skyjo_host_expand_obs(None, 0, 67, None, 0)
+    L.skyjo_host_expand_packed(None, 0, None, None, None)
+    assert L.skyjo_host_obs_record_bytes(19) == -1 and L.skyjo_host_obs_record_bytes(31) == 19
+    assert L.skyjo_host_policy(0, 0, 0, 0) == -1                            # no legal action
