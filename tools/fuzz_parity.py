@@ -8,8 +8,12 @@
     python tools/fuzz_parity.py reference SECONDS    # the LIVE reference (/root/reference, build container only) vs
                                                      # the C oracle: random injected decks (standard and dense), N = 1..12
 
-Prints every mismatch with its parameters and a final count.  Round 1: 2 507 hostsim runs and 16 778 reference games
-(3.29 M steps, 30 706 in-game reshuffles) without a mismatch."""
+    python tools/fuzz_parity.py strategy  SECONDS    # host-compiled kernels vs the C oracle on games played by the
+                                                     # hoarder / hunter / closer strategies (tests/test_strategy_games.py)
+
+Prints every mismatch with its parameters and a final count.  Round 1: 3 676 hostsim runs, 2 564 strategy games (3.58 M
+steps, 18 709 reshuffles, 3 960 column removals) and 16 778 reference games (3.29 M steps, 30 706 in-game reshuffles)
+without a mismatch."""
 import importlib.util
 import os
 import sys
@@ -89,6 +93,28 @@ def fuzz_reference(seconds):
     return bad
 
 
+def fuzz_strategy(seconds):
+    from hostsim.sim import HostSimEnv
+    import test_strategy_games as S
+    rng = np.random.default_rng(int(time.time()) ^ 0xC3C3)
+    t_end, games, steps, resh, removed, bad = time.time() + seconds, 0, 0, 0, 0, 0
+    while time.time() < t_end:
+        N, ind = int(rng.integers(1, 9)), bool(rng.integers(2))
+        pen, mr, rr = float(rng.choice([0.5, 2.0, 3.0])), float(rng.choice([0.0, 1.0])), float(rng.choice([0.0, 0.01]))
+        seed, env_id = int(rng.integers(1, 10 ** 9)), int(rng.integers(0, 10 ** 6))
+        try:
+            t, r, f = S.play_against_oracle(HostSimEnv, N, ind, pen, mr, rr, seed, env_id, np.random.default_rng(seed))
+            games, steps, resh, removed = games + 1, steps + t, resh + r, removed + f
+        except AssertionError:
+            bad += 1
+            print("MISMATCH", dict(N=N, indirect=ind, penalty=pen, seed=seed, env=env_id), flush=True)
+            traceback.print_exc()
+    print(f"strategy games, hostsim vs oracle: {games} games ok ({steps} steps, {resh} reshuffles, {removed} removals), "
+          f"{bad} mismatches")
+    return bad
+
+
 if __name__ == "__main__":
     which, seconds = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
-    sys.exit(1 if (fuzz_hostsim if which == "hostsim" else fuzz_reference)(seconds) else 0)
+    fn = {"hostsim": fuzz_hostsim, "reference": fuzz_reference, "strategy": fuzz_strategy}[which]
+    sys.exit(1 if fn(seconds) else 0)
