@@ -8,6 +8,7 @@
     python tools/fuzz_parity.py reference SECONDS    # the LIVE reference (/root/reference, build container only) vs
                                                      # the C oracle: random injected decks (standard and dense), N = 1..12
 
+    python tools/fuzz_parity.py gpu       SECONDS    # the same as hostsim, on the CUDA build (under gpurun)
     python tools/fuzz_parity.py strategy  SECONDS    # host-compiled kernels vs the C oracle on games played by the
                                                      # hoarder / hunter / closer strategies (tests/test_strategy_games.py)
 
@@ -26,15 +27,18 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 
-def fuzz_hostsim(seconds):
-    from hostsim.sim import HostSimEnv
+def fuzz_hostsim(seconds, gpu=False):
     import parity_util as P
+    if gpu:                                   # the CUDA build itself (needs a B200): warp-level staging, warp assist
+        from skyjo_rl_b200 import BatchedSkyjoEnv as HostSimEnv
+    else:
+        from hostsim.sim import HostSimEnv
     rng = np.random.default_rng(int(time.time()))
     t_end, runs, bad = time.time() + seconds, 0, 0
     while time.time() < t_end:
         N, ind, mode = int(rng.integers(1, 13)), bool(rng.integers(2)), int(rng.choice([1, 2]))
         pen, mr = float(rng.choice([0.5, 1.0, 2.0, 3.3])), float(rng.choice([-1.0, 0.0, 1.0]))
-        rr, B = float(rng.choice([0.0, 0.01, 0.25])), int(rng.integers(1, 40))
+        rr, B = float(rng.choice([0.0, 0.01, 0.25])), int(rng.integers(1, 200 if gpu else 40))
         T = int(rng.integers(60 * N + 100, 60 * N + 600))          # long enough for games to end
         params = dict(N=N, indirect=ind, mode=mode, penalty=pen, mr=mr, rr=rr, B=B, T=T)
         try:
@@ -50,7 +54,7 @@ def fuzz_hostsim(seconds):
             bad += 1
             print("MISMATCH", params, flush=True)
             traceback.print_exc()
-    print(f"hostsim vs oracle: {runs} runs ok, {bad} mismatches")
+    print(f"{'GPU' if gpu else 'hostsim'} vs oracle: {runs} runs ok, {bad} mismatches")
     return bad
 
 
@@ -116,5 +120,6 @@ def fuzz_strategy(seconds):
 
 if __name__ == "__main__":
     which, seconds = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
-    fn = {"hostsim": fuzz_hostsim, "reference": fuzz_reference, "strategy": fuzz_strategy}[which]
+    fn = {"hostsim": fuzz_hostsim, "reference": fuzz_reference, "strategy": fuzz_strategy,
+          "gpu": lambda sec: fuzz_hostsim(sec, gpu=True)}[which]
     sys.exit(1 if fn(seconds) else 0)
