@@ -114,56 +114,61 @@ def test_hostsim_matches_oracle_on_strategy_games():
     assert resh >= 10 and refunds >= 3 and steps > 3000, (steps, resh, refunds)
 
 
+def play_reference_vs_oracle(mg, N, indirect, penalty, mr, rr, deck, flips, seed, env_id, rng):
+    """One strategy-played game through the LIVE reference (dealt the injected deck with the recipe of make_golden.play,
+    its in-game reshuffles keyed like ours) and the oracle side by side; returns (steps, reshuffles, removals)."""
+    import types
+    from rlskyjo.environment.skyjo_env import SimpleSkyjoEnv
+    from rlskyjo.game.skyjo import SkyjoGame
+    mg._RESHUFFLE["ctx"] = None
+    g = SkyjoGame(num_players=N, score_penalty=penalty, observe_other_player_indirect=indirect)
+    g.players_cards = deck[: 12 * N].reshape(N, 12).astype(np.int8).copy()
+    masks = np.full((N, 12), 2, dtype=np.int8)
+    for p in range(N):
+        masks[p, flips[p, 0]] = masks[p, flips[p, 1]] = 1
+    g.players_masked = masks
+    rest = [int(x) for x in deck[12 * N:]]
+    g.discard_pile, g.drawpile = [rest[-1]], rest[:-1]
+    g._reset_start_player()
+    mg._RESHUFFLE["ctx"] = {"seed": seed, "env": env_id, "episode": 0, "q": 0, "n": 0}
+    og = O.OracleGame(N, penalty, indirect)
+    og.reset_injected(deck, flips)
+    og.set_rng_reshuffle(seed, env_id, 0)
+    hoard_for = game_plan(rng, N)
+    t = 0
+    while not g.is_terminated:
+        pid = g.expected_action[0]
+        assert og.expected_action[0] == pid
+        obs, mask = g.collect_observation(pid)
+        oo, om = og.collect_observation(pid)
+        np.testing.assert_array_equal(oo, obs, err_msg=f"obs at {t}")
+        np.testing.assert_array_equal(om, mask, err_msg=f"mask at {t}")
+        mode = ("hoard" if t % 5 else "hunt") if t < hoard_for else "close"
+        a = strategy_action(obs, mask, rng, mode, 19 if indirect else 19 + 12 * pid)
+        assert bool(g.act(pid, a)) == bool(og.act(pid, a))
+        t += 1
+    metrics = g.get_game_metrics()
+    reward = SimpleSkyjoEnv._calc_final_rewards(types.SimpleNamespace(mean_reward=mr, reward_refunded=rr), **metrics)
+    assert np.asarray(reward, np.float64).tobytes() == og.final_rewards(mr, rr).tobytes()
+    assert np.asarray(metrics["final_score"], np.float64).tobytes() == \
+        np.asarray(og.game_metrics["final_score"], np.float64).tobytes()
+    np.testing.assert_array_equal(og.players_cards, g.players_cards)
+    np.testing.assert_array_equal(og.players_masked, g.players_masked)
+    assert og.n_reshuffles == mg._RESHUFFLE["ctx"]["n"]
+    return t, og.n_reshuffles, int(np.sum(metrics["num_refunded"]))
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "rlskyjo")) or importlib.util.find_spec("numba") is None,
                     reason="the reference is only mounted in the build container")
 def test_oracle_matches_live_reference_on_strategy_games():
     spec = importlib.util.spec_from_file_location("make_golden_strategy", os.path.join(HERE, "golden", "make_golden.py"))
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
-    from rlskyjo.environment.skyjo_env import SimpleSkyjoEnv
-    from rlskyjo.game.skyjo import SkyjoGame
-    import types
-    total_resh = total_ref = 0
+    total_resh = 0
     for ci, (N, indirect, penalty, mr, rr) in enumerate(STRATEGY_CONFIGS):
         rng = np.random.default_rng(900 + ci)
-        seed, env_id = 31337 + ci, ci
         deck = mg.make_deck(rng, "dense" if ci == 2 else "standard")
         flips = np.stack([rng.choice(12, 2, replace=False) for _ in range(N)]).astype(np.uint8)
-        # the reference, dealt the injected deck (recipe of make_golden.play), its in-game reshuffles keyed like ours
-        mg._RESHUFFLE["ctx"] = None
-        g = SkyjoGame(num_players=N, score_penalty=penalty, observe_other_player_indirect=indirect)
-        g.players_cards = deck[: 12 * N].reshape(N, 12).astype(np.int8).copy()
-        masks = np.full((N, 12), 2, dtype=np.int8)
-        for p in range(N):
-            masks[p, flips[p, 0]] = masks[p, flips[p, 1]] = 1
-        g.players_masked = masks
-        rest = [int(x) for x in deck[12 * N:]]
-        g.discard_pile, g.drawpile = [rest[-1]], rest[:-1]
-        g._reset_start_player()
-        mg._RESHUFFLE["ctx"] = {"seed": seed, "env": env_id, "episode": 0, "q": 0, "n": 0}
-        og = O.OracleGame(N, penalty, indirect)
-        og.reset_injected(deck, flips)
-        og.set_rng_reshuffle(seed, env_id, 0)
-        hoard_for = game_plan(rng, N)
-        t = 0
-        while not g.is_terminated:
-            pid = g.expected_action[0]
-            assert og.expected_action[0] == pid
-            obs, mask = g.collect_observation(pid)
-            oo, om = og.collect_observation(pid)
-            np.testing.assert_array_equal(oo, obs, err_msg=f"obs at {t}")
-            np.testing.assert_array_equal(om, mask, err_msg=f"mask at {t}")
-            mode = ("hoard" if t % 5 else "hunt") if t < hoard_for else "close"
-            a = strategy_action(obs, mask, rng, mode, 19 if indirect else 19 + 12 * pid)
-            assert bool(g.act(pid, a)) == bool(og.act(pid, a))
-            t += 1
-        metrics = g.get_game_metrics()
-        reward = SimpleSkyjoEnv._calc_final_rewards(types.SimpleNamespace(mean_reward=mr, reward_refunded=rr), **metrics)
-        assert np.asarray(reward, np.float64).tobytes() == og.final_rewards(mr, rr).tobytes()
-        assert np.asarray(metrics["final_score"], np.float64).tobytes() == \
-            np.asarray(og.game_metrics["final_score"], np.float64).tobytes()
-        np.testing.assert_array_equal(og.players_cards, g.players_cards)
-        assert og.n_reshuffles == mg._RESHUFFLE["ctx"]["n"]
-        total_resh += og.n_reshuffles
-        total_ref += int(np.sum(metrics["num_refunded"]))
+        _, resh, _ = play_reference_vs_oracle(mg, N, indirect, penalty, mr, rr, deck, flips, 31337 + ci, ci, rng)
+        total_resh += resh
     assert total_resh >= 5, total_resh

@@ -9,12 +9,13 @@
                                                      # the C oracle: random injected decks (standard and dense), N = 1..12
 
     python tools/fuzz_parity.py gpu       SECONDS    # the same as hostsim, on the CUDA build (under gpurun)
+    python tools/fuzz_parity.py reference-strategy SECONDS   # the live reference vs the oracle on strategy-played games
     python tools/fuzz_parity.py strategy  SECONDS    # host-compiled kernels vs the C oracle on games played by the
                                                      # hoarder / hunter / closer strategies (tests/test_strategy_games.py)
 
-Prints every mismatch with its parameters and a final count.  Round 1: 3 676 hostsim runs, 2 564 strategy games (3.58 M
-steps, 18 709 reshuffles, 3 960 column removals) and 16 778 reference games (3.29 M steps, 30 706 in-game reshuffles)
-without a mismatch."""
+Prints every mismatch with its parameters and a final count.  Round-1 totals (no mismatch): reference 36 178 games
+(7.1 M steps, 65 872 reshuffles), reference-strategy 3 076 games (3.3 M steps, 13 402 reshuffles, 5 067 removals),
+hostsim 3 676 runs, strategy 2 564 games (3.58 M steps), gpu 45 runs."""
 import importlib.util
 import os
 import sys
@@ -118,8 +119,34 @@ def fuzz_strategy(seconds):
     return bad
 
 
+def fuzz_reference_strategy(seconds):
+    import test_strategy_games as S
+    spec = importlib.util.spec_from_file_location("make_golden_fuzz2", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    rng = np.random.default_rng(int(time.time()) ^ 0x1234)
+    t_end, games, steps, resh, removed, bad = time.time() + seconds, 0, 0, 0, 0, 0
+    while time.time() < t_end:
+        N, ind = int(rng.integers(1, 7)), bool(rng.integers(2))
+        pen, mr, rr = float(rng.choice([0.5, 2.0, 3.0])), float(rng.choice([0.0, 1.0])), float(rng.choice([0.0, 0.01]))
+        seed, env_id = int(rng.integers(1, 2 ** 40)), int(rng.integers(0, 1000))
+        kind = str(rng.choice(["standard", "dense"]))
+        deck = mg.make_deck(rng, kind)
+        flips = np.stack([rng.choice(12, 2, replace=False) for _ in range(N)]).astype(np.uint8)
+        try:
+            t, r, f = S.play_reference_vs_oracle(mg, N, ind, pen, mr, rr, deck, flips, seed, env_id, rng)
+            games, steps, resh, removed = games + 1, steps + t, resh + r, removed + f
+        except AssertionError:
+            bad += 1
+            print("MISMATCH", dict(N=N, indirect=ind, kind=kind, penalty=pen, seed=seed, env=env_id), flush=True)
+            traceback.print_exc()
+    print(f"strategy games, live reference vs oracle: {games} games ok ({steps} steps, {resh} reshuffles, "
+          f"{removed} removals), {bad} mismatches")
+    return bad
+
+
 if __name__ == "__main__":
     which, seconds = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
     fn = {"hostsim": fuzz_hostsim, "reference": fuzz_reference, "strategy": fuzz_strategy,
-          "gpu": lambda sec: fuzz_hostsim(sec, gpu=True)}[which]
+          "gpu": lambda sec: fuzz_hostsim(sec, gpu=True), "reference-strategy": fuzz_reference_strategy}[which]
     sys.exit(1 if fn(seconds) else 0)
