@@ -179,6 +179,11 @@ int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *
 /* n_steps fused launches with the uniform legal policy (random_admissible_policy.py:26-28)
  * drawn in-kernel: the loop of sample_game.py:10-21. */
 int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream);
+/* skyjo_step_random steps a batch as n independent env ranges, each on its own CUDA stream with its own
+ * refill deals (games never interact; one range's launch ramp / tail is covered by the others' CTAs).
+ * n = 0 restores the default (4 ranges from 2^18 envs, else 1; env SKYJO_RANGES overrides at creation),
+ * n = 1..8 forces it -- results are bit-identical for every n (tested against the oracle). */
+int skyjo_set_env_ranges(SkyjoHandle *h, int n);
 /* Time-major rollout buffers (device) of skyjo_rollout_random: obs int8[T, B, D];
  * action_mask int8[T, B, 26]; agent int8[T, B]; done uint8[T, B]. */
 typedef struct SkyjoRollout {
@@ -283,6 +288,18 @@ void skyjo_host_deck(uint64_t seed, uint64_t global_env, uint32_t episode, int8_
 void skyjo_host_flips(uint64_t seed, uint64_t global_env, uint32_t episode, int num_players,
                       uint8_t *out /* [N][2] */);
 int skyjo_host_policy(uint64_t seed, uint64_t global_env, uint64_t t, uint32_t legal_bits);
+/* Host twin of the in-game draw-pile reshuffle, i.e. the rule that stands in for
+ * SkyjoGame._reshuffle_discard_pile (skyjo.py:127-138, called from :361-365): permutes
+ * pile[0..len) (card values -2..12, len <= 512) in place into the order the device plays for the
+ * reshuffle_index-th reshuffle (0-based) of `episode` of `global_env`.  Python-list convention of
+ * the reference: the LAST element becomes the new discard card (`drawpile.pop()`, :137), the one
+ * before it is the first card drawn, and so on down to pile[0].  The order is sequential sampling
+ * without replacement from the pile's multiset with Philox numbers -- a uniform random permutation.
+ * A third party that drives the unmodified reference with
+ *     SkyjoGame._reshuffle_discard_pile = staticmethod(f)   # f calls this, see INTEGRATION.md
+ * gets the games the device plays.  Returns 0, or SKYJO_E_INVALID for a bad pile. */
+int skyjo_host_reshuffle(uint64_t seed, uint64_t global_env, uint32_t episode,
+                         uint32_t reshuffle_index, int8_t *pile, int len);
 /* Host half of skyjo_step_host's wire format: expands n packed words (bits 0..25 legal actions,
  * 26..27 done code, 28..31 agent) into mask int8[n,26] / agent int8[n] / done uint8[n]
  * (null outputs are skipped). */

@@ -35,6 +35,7 @@ EXPORTS = [
     "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
     "skyjo_host_policy", "skyjo_host_expand_packed", "skyjo_set_host_wire", "skyjo_host_wire_bytes",
     "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs", "skyjo_stats_allreduce",
+    "skyjo_host_reshuffle", "skyjo_set_env_ranges",
 ]
 
 
@@ -118,6 +119,7 @@ def load():
         "skyjo_seed": (i32, [vp, u64, vp]),
         "skyjo_step": (i32, [vp, vp, i32, vp]),
         "skyjo_step_random": (i32, [vp, i32, vp]),
+        "skyjo_set_env_ranges": (i32, [vp, i32]),
         "skyjo_rollout_random": (i32, [vp, i32, C.POINTER(SkyjoRollout), vp]),
         "skyjo_profile_begin": (i32, [vp]),
         "skyjo_profile_end": (i32, [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]),
@@ -143,6 +145,7 @@ def load():
         "skyjo_host_deck": (None, [u64, u64, u32, vp]),
         "skyjo_host_flips": (None, [u64, u64, u32, i32, vp]),
         "skyjo_host_policy": (i32, [u64, u64, u64, u32]),
+        "skyjo_host_reshuffle": (i32, [u64, u64, u32, u32, vp, i32]),
         "skyjo_host_expand_packed": (None, [vp, i64, vp, vp, vp]),
         "skyjo_host_obs_record_bytes": (i32, [i32]),
         "skyjo_host_pack_obs": (i64, [vp, i64, i32, vp]),

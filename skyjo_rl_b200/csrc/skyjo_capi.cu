@@ -488,6 +488,10 @@ int skyjo_reset_injected(SkyjoHandle *h, const int8_t *decks_dev, const uint8_t 
 int skyjo_seed(SkyjoHandle *h, uint64_t seed, void *stream) {
     if (!h) return fail(SKYJO_E_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
+    // a refill deal still running on deal_stream reads and bumps episode[]: it has to be over before the
+    // counters are zeroed, or the flagged envs restart at episode 1 / 2 instead of 0
+    int rc = quiesce(h, (cudaStream_t)stream);
+    if (rc) return rc;
     h->seed = seed;
     h->t = 0;
     CU(cudaMemsetAsync(h->st.episode, 0, (size_t)h->Bpad * 4, (cudaStream_t)stream));
@@ -612,6 +616,12 @@ int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream) {
     // every call ends with its window closed (the deal may still be running on deal_stream)
     prof_close_window(h, s);
     if (h->steps_since_deal > 0) return close_window(h, s, true);
+    return SKYJO_OK;
+}
+
+int skyjo_set_env_ranges(SkyjoHandle *h, int n) {
+    if (!h || n < 0 || n > HOSTIO_MAX_CHUNKS) return fail(SKYJO_E_INVALID, "env ranges must be 0 (default) .. 8");
+    h->n_ranges = n > 0 ? n : (h->B >= (1 << 18) ? 4 : 1);
     return SKYJO_OK;
 }
 
@@ -1075,6 +1085,31 @@ void skyjo_host_flips(uint64_t seed, uint64_t genv, uint32_t episode, int num_pl
         out[2 * q] = (uint8_t)a;
         out[2 * q + 1] = (uint8_t)b;
     }
+}
+
+// The device never materialises the reshuffled pile: env_step samples the remaining multiset one card per
+// draw (skyjo_core.cuh: rng_block(PURPOSE_RESHUFFLE, episode, q << 16 | remaining) -> hist_take).  This twin
+// plays the same draws forward over the whole pile and lays them out as the python list the reference
+// expects (last element = new discard card, skyjo.py:135-138).
+int skyjo_host_reshuffle(uint64_t seed, uint64_t genv, uint32_t episode, uint32_t reshuffle_index, int8_t *pile,
+                         int len) {
+    if (!pile || len < 1 || len > 512) return fail(SKYJO_E_INVALID, "pile must hold 1..512 cards");
+    int bins[15] = {0};
+    for (int i = 0; i < len; ++i) {
+        if (pile[i] < -2 || pile[i] > 12) return fail(SKYJO_E_INVALID, "pile holds a card outside -2..12");
+        bins[pile[i] + 2] += 1;
+    }
+    const uint32_t q = reshuffle_index & (uint32_t)HDR_Q_MASK;  // the header keeps 7 bits of the reshuffle index
+    for (int d = 0; d < len; ++d) {
+        const uint32_t remaining = (uint32_t)(len - d);
+        const U4 r = rng_block(seed, genv, PURPOSE_RESHUFFLE, episode, (q << 16) | remaining);
+        uint32_t idx = bounded(r.x, remaining);
+        int code = 0;  // smallest code with bins[0] + .. + bins[code] > idx (hist_take)
+        while (idx >= (uint32_t)bins[code]) idx -= (uint32_t)bins[code++];
+        bins[code] -= 1;
+        pile[len - 1 - d] = (int8_t)(code - 2);
+    }
+    return SKYJO_OK;
 }
 
 void skyjo_host_expand_packed(const uint32_t *packed, int64_t n, int8_t *mask, int8_t *agent, uint8_t *done) {

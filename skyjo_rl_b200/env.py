@@ -50,6 +50,8 @@ class BatchedSkyjoEnv:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("BatchedSkyjoEnv runs on CUDA devices only")
+        if self.device.index is None:   # "cuda" = the current device, with an explicit index from here on
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
         self.num_players = int(num_players)
         self.mean_reward = float(mean_reward)
@@ -82,7 +84,7 @@ class BatchedSkyjoEnv:
             self.rewards = torch.zeros((B, N), dtype=torch.float64, device=self.device)
             self.final_scores = torch.zeros((B, N), dtype=torch.float64, device=self.device)
         handle = C.c_void_p()
-        _lib.check(self._L.skyjo_create(C.byref(self._cfg), self.device.index or 0, B, int(seed),
+        _lib.check(self._L.skyjo_create(C.byref(self._cfg), self.device.index, B, int(seed),
                                         int(first_global_env_id), self._state.data_ptr(), nbytes,
                                         C.byref(handle)))
         self._h = handle
@@ -190,6 +192,11 @@ class BatchedSkyjoEnv:
         (the loop of rlskyjo/game/sample_game.py:10-21)."""
         assert self._has_reset, "reset() needs to be called before step"
         _lib.check(self._L.skyjo_step_random(self._h, int(n_steps), self._stream()))
+
+    def set_env_ranges(self, n=0):
+        """step_random steps the batch as n independent env ranges on n CUDA streams (0 = default: 4 from 2^18
+        envs, else 1).  Same games for every n."""
+        _lib.check(self._L.skyjo_set_env_ranges(self._h, int(n)))
 
     def rollout_random(self, n_steps, out=None):
         """The env-steps of step_random(n_steps) as multi-step launches (state in registers across
@@ -305,7 +312,12 @@ class BatchedSkyjoEnv:
 
     def last(self):
         """AECEnv.last(): (observation, cumulative reward, done, info) of agent_selection, batched.
-        Rewards are zero until an episode ends, so the cumulative reward equals `rewards`."""
+        Rewards are zero until an episode ends, so the cumulative reward equals `rewards`.
+        AEC-faithful with auto_reset=False or "next_step": the step that ends a game leaves the finisher selected,
+        with the terminal observation, as the reference's env does (skyjo_env.py:239-247).  In the default same-step
+        mode that step has already installed the next episode, so agent_selection / the observation belong to the
+        NEW game while `rewards` / `dones` still describe the finished one: read `rewards[:, seat]` per seat there
+        (what ppo.py does) instead of pairing last()'s reward with its observation."""
         sel = self.agent_selection.long().unsqueeze(1)
         reward = self.rewards.gather(1, sel).squeeze(1)
         return self.observe(), reward, self.dones, {}
@@ -405,7 +417,16 @@ class BatchedSkyjoEnv:
         }
 
     def load_state_dict(self, sd):
-        assert sd["num_envs"] == self.num_envs and sd["config"]["num_players"] == self.num_players
+        """Resume from state_dict().  Every later Philox draw (deal, reshuffle, in-kernel policy, sample) is keyed
+        by (seed, global env id) and the rewards by the config, all of which live in the handle: a checkpoint only
+        continues the same games in an env built with the same values, so a mismatch raises."""
+        mine = {k: getattr(self._cfg, k) for k, _ in _lib.SkyjoConfig._fields_}
+        diff = {k: (sd["config"].get(k), v) for k, v in mine.items() if sd["config"].get(k) != v}
+        for k, v in (("num_envs", self.num_envs), ("seed", self._seed), ("first_global_env_id", self.first_global_env_id)):
+            if sd[k] != v:
+                diff[k] = (sd[k], v)
+        if diff:
+            raise ValueError(f"checkpoint does not belong to this env (saved, this env): {diff}")
         _lib.check(self._L.skyjo_quiesce(self._h, self._stream()))
         for name in ("observations", "action_mask", "agent_selection", "done_code", "rewards", "final_scores"):
             getattr(self, name).copy_(sd[name])

@@ -167,14 +167,29 @@ class PPOTrainer:
         v_old = st.value[:T].reshape(-1)
         adv_f, ret_f = adv.reshape(-1), ret.reshape(-1)
         a_sel = adv_f[sel]
-        adv_n = (adv_f - a_sel.mean()) / (a_sel.std() + 1e-8)
+        # advantage moments over ALL ranks (every rank optimises the same objective): sum, sum of squares, count
+        mom = torch.stack([a_sel.sum(), (a_sel * a_sel).sum(), a_sel.new_tensor(float(a_sel.numel()))]).double()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(mom)
+        n_all = mom[2].clamp(min=1.0)
+        a_mean = mom[0] / n_all
+        a_std = ((mom[1] / n_all - a_mean * a_mean).clamp(min=0.0) * n_all / (n_all - 1.0).clamp(min=1.0)).sqrt()
+        adv_n = (adv_f - a_mean.to(adv_f.dtype)) / (a_std.to(adv_f.dtype) + 1e-8)
         out = {"policy_loss": 0.0, "vf_loss": 0.0, "entropy": 0.0, "kl": 0.0}
         n_upd = 0
-        mb = (sel.numel() + self.minibatches - 1) // self.minibatches
         for _ in range(self.epochs):
             perm = sel[torch.randperm(sel.numel(), device=sel.device, generator=self._gen)]
-            for k in range(0, perm.numel(), mb):
-                i = perm[k:k + mb]
+            # exactly `minibatches` chunks on every rank, whatever its count of valid transitions: the gradient
+            # all-reduces of the ranks must pair up one to one (an empty chunk contributes a zero gradient)
+            for i in torch.tensor_split(perm, self.minibatches):
+                if i.numel() == 0:
+                    self.opt.zero_grad(set_to_none=True)
+                    for prm in self.policy.parameters():
+                        prm.grad = torch.zeros_like(prm)
+                    self._sync_grads()
+                    self.opt.step()
+                    continue
                 logp, ent, v = self.evaluate(obs[i], mask[i], act[i])
                 ratio = torch.exp(logp - logp_old[i])
                 a = adv_n[i]

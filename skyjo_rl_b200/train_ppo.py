@@ -51,8 +51,11 @@ def main(argv=None):
     env.reset()
     tr = PPOTrainer(env, rollout_len=a.rollout_len, lr=a.lr, epochs=a.epochs, minibatches=a.minibatches,
                     ent_coef=a.ent_coef, seed=a.seed + rank)
+    def rank_path(path):      # env state and generator are per rank (disjoint global env ids): one file per rank
+        return path if world == 1 else f"{path}.rank{rank}"
+
     if a.resume:
-        tr.load_state_dict(torch.load(a.resume, map_location=dev, weights_only=False))
+        tr.load_state_dict(torch.load(rank_path(a.resume), map_location=dev, weights_only=False))
     for _ in range(a.iters):
         t0 = time.perf_counter()
         m = tr.train_iteration()
@@ -61,8 +64,8 @@ def main(argv=None):
         m["env_steps_per_s"] = m["env_steps"] * world / m["seconds"]
         if rank == 0:
             print(json.dumps({k: (round(v, 5) if isinstance(v, float) else v) for k, v in m.items()}), flush=True)
-    if a.checkpoint and rank == 0:
-        torch.save(tr.state_dict(), a.checkpoint)
+    if a.checkpoint:
+        torch.save(tr.state_dict(), rank_path(a.checkpoint))
     if world > 1:
         torch.distributed.destroy_process_group()
 

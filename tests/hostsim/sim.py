@@ -101,6 +101,9 @@ class HostSimEnv:
         for _ in range(n):
             self.L.hs_step(self.h, None)
 
+    def set_env_ranges(self, n=0):
+        pass    # a launch-scheduling knob of the CUDA library; the host build steps env by env
+
     def observe(self, agent):
         obs = np.empty_like(self.observations)
         mask = np.empty_like(self.action_mask)

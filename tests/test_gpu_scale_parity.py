@@ -1,0 +1,93 @@
+"""Bit parity of the BENCHMARKED code path with the oracle, at bench scale.
+
+bench.py drives `skyjo_step_random(h, 64)` on 2^20 (config 2) and 2^24 (config 3) envs.  From 2^18 envs that entry
+is `step_random_ranges` (csrc/skyjo_capi.cu): the batch stepped as 4 independent env ranges on 4 CUDA streams, each
+with its own flagged refill deals, in the phase-locked next-step reset mode.  The per-step oracle comparisons of
+tests/test_gpu_parity.py use small batches and step_random(1), i.e. the single-stream path; here the multi-stream
+path itself is compared with the oracle:
+
+  * at small batches with the range count forced (skyjo_set_env_ranges), every env, chunks of odd and even sizes;
+  * at BASELINE config 2 (N=4, 2^20 envs) and config 3 (N=8, 2^24 envs) at FULL size: >= 512 sampled envs -- runs of
+    32 consecutive envs spread over the batch, the envs either side of every range boundary, the first and the last
+    32 -- replayed on the oracle by global env id (an env's games depend only on (seed, global id)); at every chunk
+    boundary obs / mask / agent / done / float64 rewards / final scores, at the end the complete exported state
+    (hidden cards, both piles, episode index, metrics).
+
+Reference loop being reproduced: /root/reference/rlskyjo/game/sample_game.py:10-21."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from parity_util import chunked_rollout, sample_blocks  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(**kw):
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    return BatchedSkyjoEnv(**kw)
+
+
+@pytest.mark.parametrize("N,indirect,B,ranges,chunks,mode", [
+    (4, False, 700, 4, [64, 7, 13, 64, 2, 64, 64, 33, 64], 2),
+    (4, False, 700, 4, [64, 64, 5, 64, 64, 64], 1),
+    (2, True, 1000, 3, [9, 64, 64, 64, 2, 31], 2),
+    (8, False, 520, 4, [64] * 9 + [3, 64], 2),
+    (8, False, 1030, 8, [16, 64, 64, 64, 64, 64, 64, 64, 64, 64], 1),
+    (12, False, 300, 2, [64] * 12, 2),
+    (3, False, 130, 1, [2, 64, 64, 64, 64], 2),       # one range, n >= 2: the single-stream window path
+])
+def test_env_range_streams_match_oracle_on_every_env(N, indirect, B, ranges, chunks, mode):
+    steps, ended, st = chunked_rollout(_env, N, indirect, 2.0, 1.0, 0.01, B, chunks, reset_mode=mode, ranges=ranges,
+                                       first_env=12345)
+    assert ended > B // 2 and st["steps"] == steps
+    if N >= 8:
+        assert st["reshuffles"] > 0
+
+
+@pytest.mark.parametrize("N,B,chunks,mode,min_sample", [
+    (4, 1 << 20, [64] * 5, 2, 512),            # BASELINE config 2, the bench's reset mode: 320 steps
+    (4, 1 << 20, [64] * 3 + [63, 64], 1, 512),  # same-step reset (BatchedSkyjoEnv's default)
+    (8, 1 << 24, [64] * 8, 2, 512),            # BASELINE config 3 at full size: 512 steps
+])
+def test_bench_configs_match_oracle_on_sampled_envs_at_full_size(N, B, chunks, mode, min_sample):
+    ids = sample_blocks(B, n_blocks=16, width=32, ranges=4)
+    assert len(ids) >= min_sample
+    env = _env(num_envs=B, num_players=N, score_penalty=2.0, mean_reward=1.0, reward_refunded=0.0, seed=N,
+               auto_reset=mode, first_global_env_id=0)
+    steps, ended, st = chunked_rollout(None, N, False, 2.0, 1.0, 0.0, B, chunks, reset_mode=mode, ids=ids, seed=N,
+                                       env=env)
+    T = sum(chunks)
+    assert ended > len(ids) and steps > 0.98 * len(ids) * T
+    # whole-batch bookkeeping: every lockstep slot of every env is an env-step or (mode 2) a counted reset slot
+    if mode == 1:
+        assert st["steps"] == B * T
+    else:
+        waiting = int((env.done_code != 0).sum())
+        assert st["steps"] == B * T - (st["episodes"] - waiting)
+    if N == 8:
+        assert st["reshuffles"] > 0 and st["refunds"] > 0
+    assert st["illegal"] == 0 and st["truncated"] == 0
+
+
+def test_seed_after_random_stepping_restarts_the_same_games():
+    # skyjo_seed must wait for the refill deal still running on the library's side stream before it zeroes the
+    # episode counters: seed(s) after random stepping == a fresh env seeded with s, bit for bit
+    kw = dict(num_envs=5000, num_players=4, auto_reset=2)
+    a = _env(seed=1, **kw)
+    a.reset()
+    for n in (64, 3, 64):
+        a.step_random(n)
+        a.seed(99)
+        b = _env(seed=99, **kw)
+        b.reset()
+        for _ in range(3):
+            assert torch.equal(a.observations, b.observations) and torch.equal(a.agent_selection, b.agent_selection)
+            a.step_random(50)
+            b.step_random(50)
+        assert torch.equal(a.observations, b.observations) and torch.equal(a.rewards, b.rewards)
+        va, vb = a.export(0, 64), b.export(0, 64)
+        assert all(x.episode == y.episode and np.array_equal(x.players_cards, y.players_cards) for x, y in zip(va, vb))
+        b.close()
+    a.check()

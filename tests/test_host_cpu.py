@@ -237,3 +237,94 @@ def test_empty_and_invalid_inputs_are_errors_not_crashes():
     L.skyjo_host_expand_packed(None, 0, None, None, None)
     assert L.skyjo_host_obs_record_bytes(19) == -1 and L.skyjo_host_obs_record_bytes(31) == 19
     assert L.skyjo_host_policy(0, 0, 0, 0) == -1                            # no legal action
+
+
+def _host_reshuffle(L, seed, env, ep, q, pile):
+    buf = np.ascontiguousarray(pile, dtype=np.int8).copy()
+    rc = L.skyjo_host_reshuffle(seed, env, ep, q, buf.ctypes.data, len(buf))
+    assert rc == 0, L.skyjo_last_error()
+    return buf
+
+
+def test_host_reshuffle_twin_matches_oracle_and_python_restatement():
+    # the exported twin of the in-game reshuffle rule (skyjo.py:127-138 stand-in) against the oracle's and the
+    # pure-Python statement: same permutation, multiset preserved, 7-bit reshuffle index, bad piles rejected
+    import rng_twin
+    L = _lib.load()
+    rng = np.random.default_rng(5)
+    for _ in range(120):
+        n = int(rng.integers(1, 150))
+        pile = rng.integers(-2, 13, n).astype(np.int8)
+        seed, env, ep = int(rng.integers(2**62)), int(rng.integers(2**40)), int(rng.integers(2**31))
+        q = int(rng.integers(300))
+        out = _host_reshuffle(L, seed, env, ep, q, pile)
+        assert out.tolist() == O.rng_reshuffle(seed, env, ep, q, pile).tolist()
+        assert out.tolist() == rng_twin.reshuffle(seed, env, ep, q, pile.tolist())
+        assert sorted(out.tolist()) == sorted(pile.tolist())
+    bad = np.array([1, 2, 13], dtype=np.int8)
+    assert L.skyjo_host_reshuffle(1, 2, 3, 0, bad.ctypes.data, 3) != 0
+    assert L.skyjo_host_reshuffle(1, 2, 3, 0, bad.ctypes.data, 0) != 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rlskyjo"), reason="the reference is only mounted in the build container")
+def test_live_reference_patched_with_host_reshuffle_equals_oracle():
+    """What a third party does: the UNMODIFIED reference with SkyjoGame._reshuffle_discard_pile
+    replaced by a function that calls skyjo_host_reshuffle plays the games of the oracle driven by its own
+    restatement of the rule -- long 9- and 11-player games with several in-game reshuffles each."""
+    pytest.importorskip("numba")
+    import sys
+    sys.path.insert(0, "/root/reference")
+    try:
+        from rlskyjo.game.skyjo import SkyjoGame
+    finally:
+        sys.path.remove("/root/reference")
+    L = _lib.load()
+    ctx = {}
+
+    def patched(old_pile):          # (int8[L]) -> (list[L-1], list[1]), skyjo.py:127-138
+        if not ctx:
+            lst = [int(x) for x in old_pile]
+        else:
+            lst = _host_reshuffle(L, ctx["seed"], ctx["env"], 0, ctx["q"], np.asarray(old_pile, np.int8)).tolist()
+            ctx["q"] += 1
+        top = lst.pop()
+        return lst, [top]
+
+    orig = SkyjoGame.__dict__["_reshuffle_discard_pile"]
+    SkyjoGame._reshuffle_discard_pile = staticmethod(patched)
+    try:
+        rng = np.random.default_rng(77)
+        total_reshuffles = 0
+        for env, N in enumerate([9, 11, 8, 12]):
+            seed = 4242 + env
+            deck = O.rng_deck(seed, env, 0)
+            flips = O.rng_flips(seed, env, 0, N)
+            ctx.clear()
+            g = SkyjoGame(num_players=N, score_penalty=2.0, observe_other_player_indirect=False)
+            g.players_cards = deck[:12 * N].reshape(N, 12).astype(np.int8).copy()        # SURVEY 9.8 injection
+            masked = np.full((N, 12), 2, np.int8)
+            for p in range(N):
+                masked[p, flips[p]] = 1
+            g.players_masked = masked
+            rest = [int(x) for x in deck[12 * N:]]
+            g.discard_pile, g.drawpile = [rest[-1]], rest[:-1]
+            g._reset_start_player()
+            ctx.update(seed=seed, env=env, q=0)
+            og = O.OracleGame(N, 2.0, False)
+            og.reset_rng(seed, env, 0)
+            while not g.is_terminated:
+                pid = g.expected_action[0]
+                assert pid == og.expected_action[0]
+                obs, mask = g.collect_observation(pid)
+                o2, m2 = og.collect_observation(pid)
+                np.testing.assert_array_equal(obs, o2)
+                np.testing.assert_array_equal(mask, m2)
+                legal = np.flatnonzero(mask)
+                a = 24 if mask[24] and rng.random() < 0.8 else int(rng.choice(legal))   # favour the draw pile
+                assert g.act(pid, a) == og.act(pid, a)
+            assert [float(x) for x in g.game_metrics["final_score"]] == og.game_metrics["final_score"]
+            total_reshuffles += og.n_reshuffles
+            assert ctx["q"] == og.n_reshuffles
+        assert total_reshuffles >= 4
+    finally:
+        SkyjoGame._reshuffle_discard_pile = orig

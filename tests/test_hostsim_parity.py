@@ -111,3 +111,20 @@ def test_hostsim_external_actions_match_the_oracle_model(N, indirect, mode, max_
 @pytest.mark.parametrize("N,B,T,mode", [(1, 1, 120, 2), (2, 31, 200, 2), (12, 3, 700, 2), (7, 20, 450, 2)])
 def test_hostsim_small_batches_in_next_step_mode(N, B, T, mode):
     rng_rollout(HostSimEnv, N, False, 2.0, 1.0, 0.0, B, T, reset_mode=mode)
+
+
+@pytest.mark.parametrize("N,indirect,B,chunks,mode", [
+    (4, False, 96, [64, 7, 13, 64, 2, 64, 64, 33], 2), (2, True, 70, [5, 64, 64, 9, 64], 1),
+    (8, False, 40, [64] * 6 + [3, 64, 64], 2),
+])
+def test_hostsim_chunked_rollout_driver(N, indirect, B, chunks, mode):
+    # the chunk-boundary / sampled-env checker the GPU tests run at 2^20 and 2^24 envs (tests/test_gpu_scale_parity.py),
+    # here on the host-compiled kernels with a strided sample of the batch replayed on the oracle
+    from parity_util import chunked_rollout, sample_blocks
+    ids = sample_blocks(B, n_blocks=3, width=8, ranges=4)
+    assert 0 in ids and B - 1 in ids and len(ids) < B
+    steps, ended, _ = chunked_rollout(HostSimEnv, N, indirect, 2.0, 1.0, 0.01, B, chunks, reset_mode=mode, ids=ids,
+                                      first_env=5000)
+    assert ended > 0 and steps > 0
+    steps, ended, st = chunked_rollout(HostSimEnv, N, indirect, 2.0, 1.0, 0.01, 33, chunks[:4], reset_mode=mode)
+    assert st["steps"] == steps
