@@ -4,31 +4,35 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]          # N=1: this process
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one launch of the fused kernel = one env-step (SkyjoGame.act + the next agent's
-observation and action mask, i.e. one iteration of reference rlskyjo/game/sample_game.py:10-21)
-for EVERY env of the batch, with the uniform legal policy drawn in-kernel and auto-reset on.
-Auto-reset runs in the phase-locked "next_step" mode by default (include/skyjo_b200.h
-SKYJO_RESET_NEXT_STEP): the lockstep slot an env spends on its reset is NOT an env-step and is not
-counted -- every rate below divides the act() transitions counted by the kernels' statistics
-vector (SKYJO_STAT_STEPS), not launches x envs.  `--reset same_step` gives the other mode.
-Workload = BASELINE.json configs[1]: 4-player SkyJo, 2^20 lockstep envs per GPU, direct
-observations (D = 67).  Envs shard over GPUs by global env id (weak scaling: 2^20 per GPU);
-the only collective is the all-reduce of the 32-entry statistics vector every 64 steps.
+One "step" = one ITERATION of a rollout loop: 64 launches of the fused kernel -- each launch is one
+env-step (SkyjoGame.act + the next agent's observation and action mask, i.e. one iteration of reference
+rlskyjo/game/sample_game.py:10-21) for EVERY env of the batch, with the uniform legal policy drawn in-kernel and
+auto-reset on -- followed by the one collective of the path, the all-reduce of the 32-entry statistics vector, on a
+side stream.  `--steps K` therefore times K x 64 launches (K = 20 -> about 60 ms), `ms_per_step` is per iteration,
+and `value` stays in env-steps/s.
+Auto-reset runs in the phase-locked "next_step" mode by default (include/skyjo_b200.h SKYJO_RESET_NEXT_STEP): the
+lockstep slot an env spends on its reset is NOT an env-step and is not counted -- every rate below divides the act()
+transitions counted by the kernels' statistics vector (SKYJO_STAT_STEPS), not launches x envs.
+Workload = BASELINE.json configs[1]: 4-player SkyJo, 2^20 lockstep envs per GPU, direct observations (D = 67).
+Envs shard over GPUs by global env id (weak scaling: 2^20 per GPU).
 
-Printed JSON (rank 0): value = whole-job env-steps/s with state resident in HBM; e2e = the same
-metric through the host-buffer C-ABI entry (skyjo_step_host: pinned actions in, obs / mask /
-agent / done / reward out, copies inside the timed region); roofline = algorithmic bytes of one
-launch (36N + 119 B per env-step with the policy fused) / the step kernel's mean
-device time, against the measured HBM copy bandwidth; cpu_baseline = the C oracle port of the
-reference's loop on this box's host cores.
+Printed JSON (rank 0): value = whole-job env-steps/s with state resident in HBM; e2e = the same metric through the
+host-buffer C-ABI entry (skyjo_step_host: pinned actions in, obs / mask / agent / done / reward out, copies inside
+the timed region); roofline = algorithmic bytes of one launch (36N + 119 B per env-step with the
+policy fused) / the step kernel's mean device time, against the measured HBM copy bandwidth; cpu_baseline = the C
+oracle port of the reference's loop on this box's host cores, with the unmodified Python reference (baseline/_ref,
+BASELINE config 1: N=2, 10 000 games, multiprocessing.Pool) beside it; configs.c3 / configs.c5 = BASELINE configs 3
+(8 players, 2^24 envs on one GPU) and 5 (2^23 envs per GPU, 64 M on 8 GPUs) measured by the same rules in the same
+run, each with its own roofline.
 
-`--impl reference` times that CPU implementation alone (all host threads) on the same
-workload definition.  The reference is pure Python (no C sources to compile into oracle/_ref),
-so the arm runs the oracle port; see DESIGN.md.
+`--impl reference` times the CPU implementation alone (all host threads) on the same workload definition: the C
+oracle port (the reference is pure Python, nothing compiles into oracle/_ref), and reports the Python reference's
+own rate beside it.
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -39,6 +43,7 @@ sys.path.insert(0, ROOT)
 METRIC = "SkyJo env-steps/sec"
 UNIT = "env-steps/s"
 L2_MB = 126.0
+EP_LEN = {1: 46, 2: 76, 3: 106, 4: 133, 8: 240, 12: 341}     # mean act() calls per game under the uniform policy
 
 
 def algorithmic_bytes_per_step(N, indirect, action_bytes=0):
@@ -67,12 +72,12 @@ def committed_traffic(key):
     return None
 
 
-# ---- CPU baseline (oracle port) -------------------------------------------------------------
+# ---- CPU baselines -------------------------------------------------------------------------------
 _POOL = None
 
 
 def cpu_rollout(N, indirect, games_per_thread, threads, seed=0, env0=0):
-    """All threads play `games_per_thread` full games each; returns (env-steps, seconds)."""
+    """All threads play `games_per_thread` full games each on the C oracle port; returns (env-steps, seconds)."""
     global _POOL
     from concurrent.futures import ThreadPoolExecutor
 
@@ -89,43 +94,42 @@ def cpu_rollout(N, indirect, games_per_thread, threads, seed=0, env0=0):
     return steps, time.perf_counter() - t0
 
 
-def python_reference_rate(N, seconds=4.0):
-    """Optional: the unmodified Python reference (baseline/_ref copy) on one core, if importable."""
-    ref = os.path.join(ROOT, "baseline", "_ref")
-    if not os.path.isdir(os.path.join(ref, "rlskyjo")):
-        return None
+def python_reference(games=10000, timeout=600):
+    """BASELINE config 1 on the UNMODIFIED Python reference (baseline/_ref), in a fresh interpreter so that its
+    multiprocessing pool never meets this process's CUDA context: tools/python_reference_rate.py."""
+    tool = os.path.join(ROOT, "tools", "python_reference_rate.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "rlskyjo")):
+        return {"unavailable": "baseline/_ref/rlskyjo is missing (created by __graft_entry__.build() where "
+                               "/root/reference is mounted)"}
     try:
-        sys.path.insert(0, ref)
-        import numpy as np
-        from rlskyjo.game.skyjo import SkyjoGame
-        from rlskyjo.models.random_admissible_policy import policy_ra
-        g = SkyjoGame(num_players=N)
-        steps = 0
-        rng = np.random.default_rng(0)
-        for warm in (True, False):
-            t0 = time.perf_counter()
-            steps = 0
-            while time.perf_counter() - t0 < (1.0 if warm else seconds):
-                g.reset()
-                while not g.is_terminated:
-                    pid, _ = g.expected_action
-                    obs, mask = g.collect_observation(pid)
-                    g.act(pid, policy_ra(obs, mask, rng))
-                    steps += 1
-            dt = time.perf_counter() - t0
-        return steps / dt
-    except Exception:  # noqa: BLE001
-        return None
-    finally:
-        if ref in sys.path:
-            sys.path.remove(ref)
+        r = subprocess.run([sys.executable, tool, "--json", "--games", str(games), "--ref",
+                            os.path.join(ROOT, "baseline", "_ref")], capture_output=True, text=True, timeout=timeout)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": f"rc {r.returncode}: {(r.stderr or r.stdout)[-300:]}"}
+        return json.loads(line[-1])
+    except Exception as ex:  # noqa: BLE001
+        return {"unavailable": repr(ex)[:300]}
+
+
+def cpu_baseline_record(N, indirect, budget_s, with_python=True):
+    threads = os.cpu_count() or 1
+    games = max(2, int(budget_s * 1.0e6 / EP_LEN.get(N, 30 * N) / threads))
+    cpu_rollout(N, indirect, max(2, games // 10), threads)
+    s, dt = cpu_rollout(N, indirect, games, threads)
+    rec = {"value": s / dt, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"{games} full games per thread x {threads} threads ({s} env-steps), C oracle port of "
+                     "sample_game.py:10-21 with the same Philox deal and uniform legal policy"}
+    if with_python:
+        rec["python_reference"] = python_reference()
+    return rec
 
 
 # ---- clocks ------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -180,8 +184,7 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     total = args.steps + args.warmup
     # bounded sample per step so that the whole run stays near args.cpu_budget seconds
-    ep_len = {1: 46, 2: 76, 3: 106, 4: 133, 8: 240, 12: 341}.get(N, 30 * N)
-    games = int(args.cpu_budget * 1.0e6 / ep_len / max(total, 1))
+    games = int(args.cpu_budget * 1.0e6 / EP_LEN.get(N, 30 * N) / max(total, 1))
     games = max(2, min(games, 20000))
     for w in range(args.warmup):
         cpu_rollout(N, ind, games, threads, env0=w * threads * games)
@@ -193,149 +196,186 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = steps / dt
     sample = f"{games} full games per thread per step x {threads} threads, C oracle port, Philox deal + uniform legal policy"
+    cpu = {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    if not args.no_python_reference and args.gpus == 1:
+        cpu["python_reference"] = python_reference()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.players, args.envs, args.indirect, args.reset, world, args),
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "host_cores": threads,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
-    N = args.players
-    D = 31 if args.indirect else 19 + 12 * N
+def workload_config(N, B, indirect, reset, world, args):
+    D = 31 if indirect else 19 + 12 * N
     # per env-step: 1+N planes of 16 B read, plane 0 + (every other step) one row written, outputs
-    per_step_mb = args.envs * (16 * (1 + N) + 16 + 8 + D + 28) / 1e6
+    per_step_mb = B * (16 * (1 + N) + 16 + 8 + D + 28) / 1e6
     return {
-        "workload": f"{N}-player SkyJo, {args.envs} lockstep envs per GPU, uniform legal policy in-kernel, "
-                    f"fused step+mask+observe, {'indirect' if args.indirect else 'direct'} obs D={D}, "
-                    f"auto-reset ({args.reset})",
-        "reset": args.reset + (" (phase-locked: the slot an env spends on its reset is not an env-step and is not "
-                               "counted; value = counted act() transitions / time)" if args.reset == "next_step" else ""),
-        "num_players": N, "envs_per_gpu": args.envs, "global_envs": args.envs * world, "obs_len": D,
-        "parallelism": f"env-sharded x{world}, stats all-reduce every 64 steps; per GPU the batch is stepped as 4 "
+        "workload": f"{N}-player SkyJo, {B} lockstep envs per GPU, uniform legal policy in-kernel, "
+                    f"fused step+mask+observe, {'indirect' if indirect else 'direct'} obs D={D}, "
+                    f"auto-reset ({reset})",
+        "step": f"one iteration = {args.launches_per_step} env-step launches + one statistics all-reduce (side stream)",
+        "env_steps_per_step": args.launches_per_step,
+        "reset": reset + (" (phase-locked: the slot an env spends on its reset is not an env-step and is not "
+                          "counted; value = counted act() transitions / time)" if reset == "next_step" else ""),
+        "num_players": N, "envs_per_gpu": B, "global_envs": B * world, "obs_len": D,
+        "parallelism": f"env-sharded x{world}, no data-path collective; per GPU the batch is stepped as 4 "
                        "independent env ranges on 4 CUDA streams",
-        "l2": f"no flush: ~{per_step_mb:.0f} MB touched per step vs {L2_MB:.0f} MB L2 (inputs larger than L2)",
+        "l2": f"no flush: ~{per_step_mb:.0f} MB touched per launch vs {L2_MB:.0f} MB L2 (inputs larger than L2)",
         "preroll_steps": args.preroll,
     }
 
 
-def run_ours(args, rank, local_rank, world):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """torch / distributed plumbing shared by the measurements of one run"""
 
-    from skyjo_rl_b200 import BatchedSkyjoEnv, _lib
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        # the per-iteration statistics all-reduce (the only collective): the library's own ncclAllReduce on a
+        # communicator created with the NCCL torch loaded; torch.distributed.all_reduce if that cannot be created
+        self.comm = None
+        if world > 1:
+            try:
+                from skyjo_rl_b200.nccl import StatsComm
+                self.comm = StatsComm(self.dev)
+            except Exception as ex:  # noqa: BLE001
+                print(f"[bench] in-library NCCL communicator unavailable ({ex}); using torch.distributed", file=sys.stderr)
+            ok = torch.tensor([1 if self.comm is not None else 0], device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self.comm = None
 
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    N, B, K, W = args.players, args.envs, args.steps, args.warmup
-    env = BatchedSkyjoEnv(num_envs=B, num_players=N, observe_other_player_indirect=args.indirect,
-                          device=dev, seed=args.seed, first_global_env_id=rank * B, auto_reset=args.reset)
-    env.reset()
-    stats_vec = None
-    # the per-iteration statistics all-reduce (the only collective): the library's own ncclAllReduce on a
-    # communicator created with the NCCL torch loaded (skyjo_stats_allreduce); torch.distributed.all_reduce if that
-    # communicator cannot be created
-    comm = None
-    if world > 1:
-        try:
-            from skyjo_rl_b200.nccl import StatsComm
-            comm = StatsComm(dev)
-        except Exception as ex:  # noqa: BLE001
-            print(f"[bench] in-library NCCL communicator unavailable ({ex}); using torch.distributed", file=sys.stderr)
-        ok = torch.tensor([1 if comm is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            comm = None
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
 
-    def reduced_stats_tensor(e):
-        if comm is not None:
-            return e.stats_tensor(comm)
-        v = e.stats_tensor()
-        dist.all_reduce(v)
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        if self.world > 1:
+            self.dist.all_reduce(v)
         return v
 
-    def counted_steps(allreduce=True):
-        # act() transitions since the last clear_stats(), over all ranks
-        v = env.stats_tensor()
-        if world > 1 and allreduce:
-            dist.all_reduce(v)
-        return int(v[_lib.STAT_NAMES.index("steps")].item())
 
-    def run_steps(n):
-        nonlocal stats_vec
-        done = 0
-        while done < n:
-            c = min(64, n - done)
-            env.step_random(c)
-            done += c
-            if world > 1:
-                stats_vec = reduced_stats_tensor(env)
+def measure_step_loop(cx, N, B, indirect, reset, K, W, preroll, seed, profile_steps=512, keep_env=False):
+    """The timed loop of one workload: K iterations of (L step launches, one side-stream statistics all-reduce),
+    CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks; then the step kernel's
+    own launch duration for the roofline.  Returns (record, env or None)."""
+    torch, dist = cx.torch, cx.dist
+    from skyjo_rl_b200 import BatchedSkyjoEnv, _lib
+    L, world, dev = cx.args.launches_per_step, cx.world, cx.dev
+    i_steps = _lib.STAT_NAMES.index("steps")
+    env = BatchedSkyjoEnv(num_envs=B, num_players=N, observe_other_player_indirect=indirect,
+                          device=dev, seed=seed, first_global_env_id=cx.rank * B, auto_reset=reset)
+    env.reset()
+    use_lib = world == 1 or cx.comm is not None
+    last = [None]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def iteration():
+        env.step_random(L)
+        if use_lib:
+            last[0] = env.stats_allreduce_async(cx.comm)      # local reduction in stream, the collective off it
+        else:
+            last[0] = env.stats_tensor()
+            dist.all_reduce(last[0])
 
-    run_steps(args.preroll)          # desynchronise the episodes: steady-state mix of phases
-    run_steps(W)
+    done = 0
+    while done < preroll:            # desynchronise the episodes: steady-state mix of game stages
+        env.step_random(min(L, preroll - done))
+        done += L
+    for _ in range(W):
+        iteration()
+    env.stats_allreduce_wait()
     env.clear_stats()
     l0 = env.launch_count
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(cx.local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    cx.barrier()
     sampler.start()
     ev0.record()
-    run_steps(K)
+    for _ in range(K):
+        iteration()
+    env.stats_allreduce_wait()       # the timed region ends when the last all-reduce has landed
     ev1.record()
-    barrier()
+    cx.barrier()
     clocks = sampler.stop()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    ms = cx.max_over_ranks(ev0.elapsed_time(ev1))
     launches = env.launch_count - l0
-    counted = counted_steps()                 # == B * world * K in same_step mode
+    reduced = last[0].clone()        # the library's all-reduced vector of the last iteration = the whole region
+    check = cx.sum_over_ranks(env.stats_tensor())
+    assert torch.equal(reduced, check), "side-stream statistics all-reduce disagrees with torch.distributed.all_reduce"
+    counted = int(check[i_steps].item())
+    stats = dict(zip(_lib.STAT_NAMES, check.tolist()))
     value = counted / (ms * 1e-3)
-    stats = env.stats(all_reduce=world > 1)   # statistics of the timed region
-    if comm is not None:                       # the in-library all-reduce against torch.distributed's
-        assert env.stats(comm=comm) == stats, "skyjo_stats_allreduce disagrees with torch.distributed.all_reduce"
-    counted_frac = counted / float(B * world * K)
 
     # roofline of the dominant kernel: mean device time of a step launch (event pair per window of back-to-back launches)
     env.clear_stats()
-    prof = env.step_random_profile(min(K, 512))
+    prof = env.step_random_profile(min(K * L, profile_steps))
     step_us = 1e3 * prof["step_ms"] / max(prof["step_launches"], 1)
-    # algorithmic bytes of one launch = bytes per env-step x env-steps the launch plays (envs in a reset slot
-    # move state but play no step: they are not credited)
-    alg = algorithmic_bytes_per_step(N, args.indirect) * counted_steps(False) / max(prof["step_launches"], 1)
+    # algorithmic bytes of one launch = bytes per env-step x env-steps the launch plays (envs in a reset slot move
+    # state but play no step: they are not credited)
+    bps = algorithmic_bytes_per_step(N, indirect)
+    alg = bps * int(env.stats_tensor()[i_steps].item()) / max(prof["step_launches"], 1)
     peak, peak_src = hbm_peak()
     achieved = alg / (step_us * 1e-6) / 1e9
-    key = f"step_N{N}_{'indirect' if args.indirect else 'direct'}_B{B}"
-    loop_gbs = algorithmic_bytes_per_step(N, args.indirect) * (counted / world) / (ms * 1e-3) / 1e9
+    key = f"step_N{N}_{'indirect' if indirect else 'direct'}_B{B}"
     traffic = committed_traffic(key)
+    loop_gbs = bps * (counted / world) / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "skyjo::step_kernel", "kernel_us": step_us,
                 # the int8 planes move fewer bytes than SURVEY 8(d)'s accounting (80 B of planes read per 4-player
                 # env-step instead of 120, ...): the DRAM bytes ncu measured per launch over the same kernel time
                 "traffic_frac": (traffic / (step_us * 1e-6) / 1e9 / peak) if traffic else None,
-                "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                "algorithmic_bytes_per_env_step": bps, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                 "deal_kernel_share": prof["deal_ms"] / max(prof["deal_ms"] + prof["step_ms"], 1e-9),
-                "note": "kernel_us = mean duration of a full-batch step launch on one stream: CUDA events bracket every window "
-                        "of 8 back-to-back launches between two refill deals (no event between launches; the deals, "
-                        "in stream order, are timed by their own pairs); the timed loop behind `value` steps the batch "
-                        "as 4 env ranges on 4 streams, so that one range's launch ramp / tail is covered by the others",
+                "note": "kernel_us = mean duration of a full-batch step launch on one stream: CUDA events bracket every "
+                        "window of 8 back-to-back launches between two refill deals (no event between launches; the "
+                        "deals, in stream order, are timed by their own pairs); the timed loop behind `value` steps "
+                        "the batch as 4 env ranges on 4 streams, so that one range's launch ramp / tail is covered by "
+                        "the others",
                 "loop_frac": loop_gbs / peak,
-                "loop_frac_note": "same algorithmic bytes / whole timed loop (refill deals and stats included): "
+                "loop_frac_note": "same algorithmic bytes / whole timed loop (refill deals and statistics included): "
                                   "a lower bound of the step kernel's fraction inside the loop"}
     env.check()
+    rec = {"value": value, "unit": UNIT, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "us_per_launch": 1e3 * ms / (K * L), "timed_region_s": ms * 1e-3, "env_steps_per_step": L,
+           "gpu_launches": launches, "counted_env_steps": counted, "counted_frac": counted / float(B * world * K * L),
+           "roofline": roofline, "clocks": clocks,
+           "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")}}
+    if not keep_env:
+        env.close()
+        del env
+        torch.cuda.empty_cache()
+        env = None
+    return rec, env
+
+
+def run_ours(args, rank, local_rank, world):
+    cx = Ctx(args, rank, local_rank, world)
+    torch, dist, dev = cx.torch, cx.dist, cx.dev
+    from skyjo_rl_b200 import BatchedSkyjoEnv, _lib
+    N, B, K, W, L = args.players, args.envs, args.steps, args.warmup, args.launches_per_step
+
+    main, env = measure_step_loop(cx, N, B, args.indirect, args.reset, K, W, args.preroll, args.seed, keep_env=True)
+    peak = main["roofline"]["peak"]
 
     # the same env-steps as multi-step launches (rollout_kernel: state in registers across 8 steps, every
     # step's obs / mask / agent / done stored into slice t of time-major rollout tensors)
@@ -344,105 +384,97 @@ def run_ours(args, rank, local_rank, world):
         D = env.obs_len
         T = min(args.rollout_steps, int(8e9 // (B * (D + 28))) // 8 * 8)
         if T >= 8:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ro = env.rollout_random(T)
-            reps = max(1, min(K, 1024) // T)
+            reps = max(1, min(K * L, 1024) // T)
             for _ in range(2):
                 env.rollout_random(T, ro)
             env.clear_stats()
-            barrier()
+            cx.barrier()
             ev0.record()
             for _ in range(reps):
                 env.rollout_random(T, ro)
-                if world > 1:
-                    reduced_stats_tensor(env)
+                env.stats_allreduce_async(cx.comm) if (world == 1 or cx.comm is not None) else None
+            env.stats_allreduce_wait()
             ev1.record()
-            barrier()
-            rms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(rms, op=dist.ReduceOp.MAX)
-            rcounted = counted_steps()
-            rms = float(rms.item()) / (reps * T)
+            cx.barrier()
+            rms = cx.max_over_ranks(ev0.elapsed_time(ev1)) / (reps * T)
+            rcounted = int(cx.sum_over_ranks(env.stats_tensor())[_lib.STAT_NAMES.index("steps")].item())
             env.profile_begin()
             for _ in range(reps):
                 env.rollout_random(T, ro)
             rp = env.profile_end()
             env.check()
-            rollout = {"value": rcounted / (rms * 1e-3 * reps * T), "unit": UNIT, "ms_per_step": rms,
+            rollout = {"value": rcounted / (rms * 1e-3 * reps * T), "unit": UNIT, "ms_per_env_step": rms,
                        "kernel": "skyjo::rollout_kernel", "env_steps_per_launch": 8, "rollout_len": T,
                        "kernel_us_per_env_step": 1e3 * rp["step_ms"] / (reps * T),
                        "hbm_bytes_written_per_env_step": D + 28,
                        "note": "state stays in registers for 8 consecutive env-steps per launch; every step's obs, "
                                "mask, agent and done are stored into slice t of [T,B,...] rollout tensors"}
             del ro
-
-    # the other reset mode, same workload and timing rules, so that both figures come from one run
-    other = None
-    if args.other_reset_steps > 0:
-        mode2 = "same_step" if args.reset == "next_step" else "next_step"
-        env2 = BatchedSkyjoEnv(num_envs=B, num_players=N, observe_other_player_indirect=args.indirect,
-                               device=dev, seed=args.seed, first_global_env_id=rank * B, auto_reset=mode2)
-        env2.reset()
-        K2 = min(K, args.other_reset_steps)
-        env2.step_random(args.preroll)
-        env2.step_random(max(W, 3))
-        env2.clear_stats()
-        barrier()
-        ev0.record()
-        env2.step_random(K2)
-        ev1.record()
-        barrier()
-        ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-        v2 = env2.stats_tensor()
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-            dist.all_reduce(v2)
-        c2 = int(v2[_lib.STAT_NAMES.index("steps")].item())
-        env2.clear_stats()
-        prof2 = env2.step_random_profile(min(K2, 256))
-        us2 = 1e3 * prof2["step_ms"] / max(prof2["step_launches"], 1)
-        alg2 = algorithmic_bytes_per_step(N, args.indirect) * int(env2.stats()["steps"]) / max(prof2["step_launches"], 1)
-        env2.check()
-        other = {"reset": mode2, "value": c2 / (float(ms2.item()) * 1e-3), "unit": UNIT, "steps": K2,
-                 "ms_per_step": float(ms2.item()) / K2, "kernel_us": us2, "frac": alg2 / (us2 * 1e-6) / 1e9 / peak}
-        env2.close()
-        del env2
-
-    # BASELINE config 4: the action-mask MLP policy (library GEMMs) consuming obs / mask in place
-    policy_rollout = None
-    if args.policy_steps > 0 and rank == 0:
-        policy_rollout = run_policy_rollout(args, dev)
+            torch.cuda.empty_cache()
 
     # end to end through the host-buffer C-ABI entry
     e2e = None
     if args.e2e_steps > 0:
         e2e = run_e2e(args, env, dev, rank, world)
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+
+    # the other reset mode, same workload and timing rules, so that both figures come from one run
+    other = None
+    if args.other_reset_steps > 0:
+        mode2 = "same_step" if args.reset == "next_step" else "next_step"
+        r2, _ = measure_step_loop(cx, N, B, args.indirect, mode2, max(1, min(K, args.other_reset_steps)), max(W, 3),
+                                  args.preroll, args.seed, profile_steps=256)
+        other = {"reset": mode2, "value": r2["value"], "unit": UNIT, "steps": r2["steps"], "ms_per_step": r2["ms_per_step"],
+                 "us_per_launch": r2["us_per_launch"], "kernel_us": r2["roofline"]["kernel_us"],
+                 "frac": r2["roofline"]["frac"]}
+
+    # BASELINE configs 3 and 5 by the same rules, in the same run (one GPU: config 3; every N: config 5's shard)
+    configs = {}
+    if not args.no_configs:
+        if world == 1:
+            K3 = max(7, min(K, 10))         # >= 448 launches of 2^24 8-player envs (~1.07 ms each)
+            c3, _ = measure_step_loop(cx, 8, 1 << 24, False, args.reset, K3, 2, args.preroll, args.seed + 3,
+                                      profile_steps=64)
+            c3["config"] = workload_config(8, 1 << 24, False, args.reset, 1, args)
+            c3["baseline_config"] = "configs[2]: 8-player SkyJo, 16M envs on 1 B200"
+            configs["c3"] = c3
+        K5 = max(7, min(K, 20))
+        c5, _ = measure_step_loop(cx, 4, 1 << 23, False, args.reset, K5, 2, args.preroll, args.seed + 5,
+                                  profile_steps=128)
+        c5["config"] = workload_config(4, 1 << 23, False, args.reset, world, args)
+        c5["baseline_config"] = ("configs[4]: 64M envs sharded across 8 B200 with the statistics all-reduce -- 2^23 "
+                                 f"envs per GPU, here {world} GPU(s) = {world << 23} envs")
+        c5["n_gpus"] = world
+        configs["c5"] = c5
+
+    # BASELINE config 4: the action-mask MLP policy consuming obs / mask in place
+    policy_rollout = None
+    if args.policy_steps > 0 and rank == 0:
+        policy_rollout = run_policy_rollout(args, dev)
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            ep_len = {1: 46, 2: 76, 3: 106, 4: 133, 8: 240, 12: 341}.get(N, 30 * N)
-            games = max(2, int(args.cpu_budget * 1.0e6 / ep_len / threads))
-            cpu_rollout(N, args.indirect, max(2, games // 10), threads)
-            s, dt = cpu_rollout(N, args.indirect, games, threads)
-            cpu = {"value": s / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{games} full games per thread x {threads} threads ({s} env-steps), C oracle port of "
-                             "sample_game.py:10-21 with the same Philox deal and uniform legal policy",
-                   "note": "the Python reference itself (numba JIT, cannot travel to this box) ran 2.0-2.3e4 env-steps/s "
-                           "per core in the build container: profiles/r1_v7_python_reference_container.txt"}
-            pr = python_reference_rate(N) if args.python_reference else None
-            if pr:
-                cpu["python_reference_1core"] = pr
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is timed at N = 1 only
+            cpu = cpu_baseline_record(N, args.indirect, args.cpu_budget, with_python=not args.no_python_reference)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "int8", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout,
-            "counted_env_steps": counted, "counted_frac": counted_frac, "other_reset_mode": other,
-            "policy_rollout": policy_rollout,
-            "stats_allreduce": None if world == 1 else ("skyjo_stats_allreduce (in-library ncclAllReduce, every 64 steps)"
-                                                        if comm is not None else "torch.distributed.all_reduce"),
-            "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")},
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "int8", "data": "synthetic",
+            "config": workload_config(N, B, args.indirect, args.reset, world, args),
+            "clocks": main["clocks"], "e2e": e2e, "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
+            "cpu_baseline": cpu, "rollout": rollout, "env_steps_per_step": L, "us_per_launch": main["us_per_launch"],
+            "timed_region_s": main["timed_region_s"], "counted_env_steps": main["counted_env_steps"],
+            "counted_frac": main["counted_frac"], "other_reset_mode": other, "policy_rollout": policy_rollout,
+            "configs": configs, "host_cores": os.cpu_count(),
+            "stats_allreduce": ("skyjo_stats_allreduce_async: device-side reduction in stream, "
+                                + ("in-library ncclAllReduce" if world > 1 else "single-rank copy")
+                                + " on a side stream, once per iteration") if (world == 1 or cx.comm is not None)
+                               else "torch.distributed.all_reduce",
+            "episode_stats": main["episode_stats"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -545,24 +577,28 @@ def run_e2e(args, env, dev, rank, world):
     e.check()
     assert st["illegal"] == 0, "replayed actions must be legal"
     # bytes that cross the link per step (csrc/skyjo_hostio.cuh), as counted by the library from the copies it
-    # queues: one compact observation record (12 + 6 R + ceil(R / 2) bytes for a row of 19 + 12 R) and one packed
-    # mask + agent + done word per env, an 8-byte count; plus one {env, N rewards} entry (written by the pack kernel
-    # straight into host-mapped memory) per episode that ended
+    # queues: the observation row and one packed mask + agent + done word per env, an 8-byte count; plus one
+    # {env, N rewards} entry (written by the pack kernel straight into host-mapped memory) per episode that ended
     ended_per_step = (st["episodes"] + st["truncated"]) / float(T * world)
     d2h = e.host_wire_bytes + int(ended_per_step * (8 + 8 * N))
-    return {"value": st["steps"] / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": B,
-            "d2h_bytes_per_step": d2h, "steps": T,
-            "host_buffer_bytes_filled_per_step": B * (D + 26 + 1 + 1 + 8 * N),
-            "wire_bytes_per_env": round(e.host_wire_bytes / float(B), 2),
-            "api": "skyjo_step_host (C ABI) via BatchedSkyjoEnv.step_host, pinned host buffers: obs int8[B,D], "
-                   "mask int8[B,26], agent, done, reward f64[B,N] all filled every step"}
+    out = {"value": st["steps"] / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": B,
+           "d2h_bytes_per_step": d2h, "steps": T, "ms_per_call": 1e3 * float(dt.item()) / T,
+           "host_buffer_bytes_filled_per_step": B * (D + 26 + 1 + 1 + 8 * N),
+           "wire_bytes_per_env": round(e.host_wire_bytes / float(B), 2),
+           "api": "skyjo_step_host (C ABI) via BatchedSkyjoEnv.step_host, pinned host buffers: obs int8[B,D], "
+                  "mask int8[B,26], agent, done, reward f64[B,N] all filled every step; one call = one env-step of "
+                  "every env (wall clock around the calls, max over ranks)"}
+    e.close()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=60, help="timed iterations of --launches-per-step env-step launches")
+    ap.add_argument("--warmup", type=int, default=5, help="untimed iterations (after --preroll single steps)")
+    ap.add_argument("--launches-per-step", type=int, default=64,
+                    help="env-step launches per iteration (one statistics all-reduce closes each iteration)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--players", type=int, default=4)
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
@@ -573,13 +609,14 @@ def main():
                     help="auto-reset mode (SKYJO_RESET_*): next_step = phase-locked, reset slots are not counted")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--rollout-steps", type=int, default=64, help="rollout length T of the multi-step path (0 = skip)")
-    ap.add_argument("--other-reset-steps", type=int, default=1000,
-                    help="also time this many steps in the other auto-reset mode (0 = skip)")
+    ap.add_argument("--other-reset-steps", type=int, default=20,
+                    help="also time up to this many iterations in the other auto-reset mode (0 = skip)")
     ap.add_argument("--policy-steps", type=int, default=24, help="steps of the torch-policy rollout, config 4 (0 = skip)")
     ap.add_argument("--policy-envs", type=int, default=1 << 18)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="CPU-seconds of oracle work (baseline sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--python-reference", action="store_true")
+    ap.add_argument("--no-python-reference", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 3 / 5 sub-records")
     ap.add_argument("--global-envs", type=int, default=0,
                     help="strong scaling (SURVEY 8d C5): total envs fixed, split evenly over the GPUs (overrides --envs)")
     args = ap.parse_args()

@@ -255,6 +255,14 @@ int skyjo_stats_host(SkyjoHandle *h, int64_t *out_host, void *stream);
  * NCCL is resolved at run time from the libnccl already loaded in the process (torch's, or one the
  * caller opened), never linked: fails with SKYJO_E_INVALID if there is none. */
 int skyjo_stats_allreduce(SkyjoHandle *h, void *nccl_comm, int64_t *out_dev, void *stream);
+/* The same collective off the caller's stream: `stream` only runs the one-CTA device-side reduction
+ * (a snapshot of the counters at that point); the ncclAllReduce into out_dev is queued on a stream the library
+ * owns, so launches queued on `stream` afterwards never wait for a peer rank.  out_dev is valid once
+ * skyjo_stats_allreduce_wait has made a stream wait for it (or after skyjo_destroy); keep it alive and unread
+ * until then, and alternate between two buffers when issuing a call per iteration.  nccl_comm == NULL sums over
+ * one rank (a device copy), so single-GPU loops have the same shape. */
+int skyjo_stats_allreduce_async(SkyjoHandle *h, void *nccl_comm, int64_t *out_dev, void *stream);
+int skyjo_stats_allreduce_wait(SkyjoHandle *h, void *stream);
 int skyjo_stats_clear(SkyjoHandle *h, void *stream);
 
 /* Policy side of a rollout (BASELINE config 4): masked softmax + categorical sample of one action

@@ -35,7 +35,7 @@ EXPORTS = [
     "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
     "skyjo_host_policy", "skyjo_host_expand_packed", "skyjo_set_host_wire", "skyjo_host_wire_bytes",
     "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs", "skyjo_stats_allreduce",
-    "skyjo_host_reshuffle", "skyjo_set_env_ranges",
+    "skyjo_host_reshuffle", "skyjo_set_env_ranges", "skyjo_stats_allreduce_async", "skyjo_stats_allreduce_wait",
 ]
 
 
@@ -133,6 +133,8 @@ def load():
         "skyjo_stats_device": (i32, [vp, vp, vp]),
         "skyjo_stats_host": (i32, [vp, vp, vp]),
         "skyjo_stats_allreduce": (i32, [vp, vp, vp, vp]),
+        "skyjo_stats_allreduce_async": (i32, [vp, vp, vp, vp]),
+        "skyjo_stats_allreduce_wait": (i32, [vp, vp]),
         "skyjo_stats_clear": (i32, [vp, vp]),
         "skyjo_sample_actions": (i32, [vp, vp, vp, u64, vp, vp, vp, vp]),
         "skyjo_quiesce": (i32, [vp, vp]),

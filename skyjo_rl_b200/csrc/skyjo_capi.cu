@@ -60,6 +60,13 @@ struct SkyjoHandle {
     unsigned long long seed, first_env;
     DeviceState st;
     long long *stats_tmp;  // device int64[NUM_STATS]
+    // skyjo_stats_allreduce_async: local sums (double-buffered) reduced on the caller's stream, the collective on
+    // stats_stream; ev_ar_done[k] = the all-reduce that read stats_ar[k] has finished
+    long long *stats_ar;   // device int64[2][NUM_STATS]
+    bool ar_ready, ar_pending[2];
+    int ar_slot;
+    cudaStream_t stats_stream;
+    cudaEvent_t ev_ar_ready, ev_ar_done[2];
     SkyjoOutputs outs;
     bool bound;
     int bulk_ok;
@@ -158,7 +165,7 @@ static bool config_ok(const SkyjoConfig *c) {
 }
 
 struct Layout {
-    long long planes, next_planes, pile, episode, needs_deal, stats, stats_tmp, errflag, total;
+    long long planes, next_planes, pile, episode, needs_deal, stats, stats_tmp, stats_ar, errflag, total;
 };
 static Layout layout_for(int N, long long B) {
     const long long Bpad = align_up(B, ENV_PAD);
@@ -172,6 +179,7 @@ static Layout layout_for(int N, long long B) {
     L.needs_deal = off;  off = align_up(off + 2 * Bpad, 256);
     L.stats = off;       off = align_up(off + (long long)STAT_SLOTS * NUM_STATS * 8, 256);
     L.stats_tmp = off;   off = align_up(off + NUM_STATS * 8, 256);
+    L.stats_ar = off;    off = align_up(off + 2 * NUM_STATS * 8, 256);
     L.errflag = off;     off = align_up(off + 4, 256);
     L.total = off;
     return L;
@@ -241,6 +249,10 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     if (h->n_ranges > HOSTIO_MAX_CHUNKS) h->n_ranges = HOSTIO_MAX_CHUNKS;
     h->st.stats = (unsigned long long *)(base + L.stats);
     h->stats_tmp = (long long *)(base + L.stats_tmp);
+    h->stats_ar = (long long *)(base + L.stats_ar);
+    h->ar_ready = false;
+    h->ar_pending[0] = h->ar_pending[1] = false;
+    h->ar_slot = 0;
     h->st.errflag = (uint32_t *)(base + L.errflag);
     h->bound = false;
     h->bulk_ok = 0;
@@ -318,6 +330,14 @@ int skyjo_destroy(SkyjoHandle *h) {
         cudaEventDestroy(h->ev_deal[0]);
         cudaEventDestroy(h->ev_deal[1]);
         cudaStreamDestroy(h->deal_stream);
+    }
+    if (h && h->ar_ready) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stats_stream);
+        cudaEventDestroy(h->ev_ar_ready);
+        cudaEventDestroy(h->ev_ar_done[0]);
+        cudaEventDestroy(h->ev_ar_done[1]);
+        cudaStreamDestroy(h->stats_stream);
     }
     if (h) hostio_release(h);
     delete h;
@@ -942,30 +962,92 @@ int skyjo_stats_device(SkyjoHandle *h, int64_t *out_dev, void *stream) {
 // communicator, off the step path.  NCCL is not a link-time dependency: the symbols are taken from whichever
 // libnccl the process has loaded (torch's bundled one under torch.distributed, or one the caller dlopen'ed with
 // RTLD_GLOBAL), so the communicator and the call always belong to the same NCCL build.
-int skyjo_stats_allreduce(SkyjoHandle *h, void *nccl_comm, int64_t *out_dev, void *stream) {
-    if (!h || !nccl_comm || !out_dev) return fail(SKYJO_E_INVALID, "null argument");
-    typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
-    typedef const char *(*errstr_fn)(int);
-    static allreduce_fn all_reduce = nullptr;
-    static errstr_fn err_string = nullptr;
-    if (!all_reduce) {
-        all_reduce = (allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
-        err_string = (errstr_fn)dlsym(RTLD_DEFAULT, "ncclGetErrorString");
-        if (!all_reduce) {
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*nccl_errstr_fn)(int);
+static nccl_allreduce_fn g_nccl_all_reduce = nullptr;
+static nccl_errstr_fn g_nccl_err_string = nullptr;
+
+static int nccl_resolve() {
+    if (!g_nccl_all_reduce) {
+        g_nccl_all_reduce = (nccl_allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        g_nccl_err_string = (nccl_errstr_fn)dlsym(RTLD_DEFAULT, "ncclGetErrorString");
+        if (!g_nccl_all_reduce) {
             if (void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD)) {  // loaded RTLD_LOCAL
-                all_reduce = (allreduce_fn)dlsym(lib, "ncclAllReduce");
-                err_string = (errstr_fn)dlsym(lib, "ncclGetErrorString");
+                g_nccl_all_reduce = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+                g_nccl_err_string = (nccl_errstr_fn)dlsym(lib, "ncclGetErrorString");
             }
         }
     }
-    if (!all_reduce) return fail(SKYJO_E_INVALID, "NCCL is not loaded in this process (ncclAllReduce not found)");
-    int rc = skyjo_stats_device(h, out_dev, stream);
-    if (rc) return rc;
+    if (!g_nccl_all_reduce) return fail(SKYJO_E_INVALID, "NCCL is not loaded in this process (ncclAllReduce not found)");
+    return SKYJO_OK;
+}
+
+static int nccl_sum_i64(const void *src, void *dst, void *comm, cudaStream_t s) {
     const int ncclInt64 = 4, ncclSum = 0;  // nccl.h: ncclDataType_t / ncclRedOp_t
-    const int nrc = all_reduce(out_dev, out_dev, (size_t)NUM_STATS, ncclInt64, ncclSum, nccl_comm, (cudaStream_t)stream);
-    if (nrc != 0) {
-        return fail(SKYJO_E_NCCL, "ncclAllReduce failed: %s", err_string ? err_string(nrc) : "unknown NCCL error");
+    const int nrc = g_nccl_all_reduce(src, dst, (size_t)NUM_STATS, ncclInt64, ncclSum, comm, s);
+    if (nrc != 0)
+        return fail(SKYJO_E_NCCL, "ncclAllReduce failed: %s", g_nccl_err_string ? g_nccl_err_string(nrc) : "unknown NCCL error");
+    return SKYJO_OK;
+}
+
+int skyjo_stats_allreduce(SkyjoHandle *h, void *nccl_comm, int64_t *out_dev, void *stream) {
+    if (!h || !nccl_comm || !out_dev) return fail(SKYJO_E_INVALID, "null argument");
+    int rc = nccl_resolve();
+    if (rc) return rc;
+    rc = skyjo_stats_device(h, out_dev, stream);
+    if (rc) return rc;
+    return nccl_sum_i64(out_dev, out_dev, nccl_comm, (cudaStream_t)stream);
+}
+
+// The same collective OFF the caller's stream ("on a side stream after a device-side reduction").  On
+// `stream` only the one-CTA reduction of the 256 replicated counter vectors into stats_ar[k] runs (a snapshot at
+// this point of the stream, ~3 us); the ncclAllReduce -- a rendezvous with every other rank -- runs on the
+// library's stats stream behind an event, so the step launches queued on `stream` afterwards never wait for a
+// peer.  The two stats_ar buffers alternate: buffer k is rewritten two calls later, after `stream` has waited for
+// the collective that read it (long finished by then).
+int skyjo_stats_allreduce_async(SkyjoHandle *h, void *nccl_comm, int64_t *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(SKYJO_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    int rc = nccl_comm ? nccl_resolve() : SKYJO_OK;
+    if (rc) return rc;
+    if (!h->ar_ready) {
+        CU(cudaStreamCreateWithFlags(&h->stats_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_ar_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_ar_done[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_ar_done[1], cudaEventDisableTiming));
+        h->ar_ready = true;
     }
+    cudaStream_t s = (cudaStream_t)stream, ss = h->stats_stream;
+    const int k = h->ar_slot;
+    if (h->ar_pending[k]) {
+        CU(cudaStreamWaitEvent(s, h->ev_ar_done[k], 0));
+        h->ar_pending[k] = false;
+    }
+    long long *local = h->stats_ar + (size_t)k * NUM_STATS;
+    rc = skyjo_stats_device(h, (int64_t *)local, stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev_ar_ready, s));
+    CU(cudaStreamWaitEvent(ss, h->ev_ar_ready, 0));
+    if (nccl_comm) {
+        rc = nccl_sum_i64(local, out_dev, nccl_comm, ss);
+        if (rc) return rc;
+    } else {  // one rank: the sum is the local vector
+        CU(cudaMemcpyAsync(out_dev, local, NUM_STATS * 8, cudaMemcpyDeviceToDevice, ss));
+    }
+    CU(cudaEventRecord(h->ev_ar_done[k], ss));
+    h->ar_pending[k] = true;
+    h->ar_slot = k ^ 1;
+    return SKYJO_OK;
+}
+
+int skyjo_stats_allreduce_wait(SkyjoHandle *h, void *stream) {
+    if (!h) return fail(SKYJO_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    for (int k = 0; k < 2; ++k)
+        if (h->ar_pending[k]) {
+            CU(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_ar_done[k], 0));
+            h->ar_pending[k] = false;
+        }
     return SKYJO_OK;
 }
 

@@ -354,6 +354,24 @@ class BatchedSkyjoEnv:
             _lib.check(self._L.skyjo_stats_device(self._h, out.data_ptr(), self._stream()))
         return out
 
+    def stats_allreduce_async(self, comm=None):
+        """Per-iteration statistics all-reduce off the step path (skyjo_stats_allreduce_async): the env's stream only
+        runs the one-CTA local reduction, the ncclAllReduce over `comm` (a StatsComm; None = this rank alone) runs on
+        a side stream the library owns.  Returns the int64[32] device tensor the sum lands in -- two tensors
+        alternate -- valid after stats_allreduce_wait()."""
+        if not hasattr(self, "_ar_out"):
+            self._ar_out = [torch.zeros(_lib.NUM_STATS, dtype=torch.int64, device=self.device) for _ in range(2)]
+            self._ar_k = 0
+        out = self._ar_out[self._ar_k]
+        self._ar_k ^= 1
+        _lib.check(self._L.skyjo_stats_allreduce_async(self._h, comm.handle if comm is not None else None,
+                                                       out.data_ptr(), self._stream()))
+        return out
+
+    def stats_allreduce_wait(self):
+        """The env's stream waits for every statistics all-reduce still in flight on the side stream."""
+        _lib.check(self._L.skyjo_stats_allreduce_wait(self._h, self._stream()))
+
     def stats(self, all_reduce=False, group=None, comm=None):
         """Episode statistics as a dict.  With all_reduce=True the vector is summed over the
         ranks of `group` with torch.distributed (NCCL) first -- the only collective of the env,

@@ -91,3 +91,23 @@ def test_seed_after_random_stepping_restarts_the_same_games():
         assert all(x.episode == y.episode and np.array_equal(x.players_cards, y.players_cards) for x, y in zip(va, vb))
         b.close()
     a.check()
+
+
+def test_side_stream_stats_allreduce_snapshots_iteration_boundaries():
+    # skyjo_stats_allreduce_async (one rank: the collective degenerates to a copy on the side stream): the vector
+    # that lands is the snapshot at the call, whatever is queued behind it, and the two buffers alternate
+    env = _env(num_envs=1 << 16, num_players=4, seed=3, auto_reset=2)
+    env.reset()
+    want, got = [], []
+    for it in range(6):
+        env.step_random(64)
+        want.append(env.stats_tensor().clone())
+        got.append(env.stats_allreduce_async(None))
+        env.step_random(17)                       # queued behind the snapshot: must not leak into it
+        if it % 2 == 1:
+            env.stats_allreduce_wait()
+            torch.cuda.synchronize()
+            assert torch.equal(got[-2], want[-2]) and torch.equal(got[-1], want[-1])
+            assert got[-1].data_ptr() != got[-2].data_ptr()
+    assert int(want[-1][16]) > int(want[0][16]) > 0
+    env.check()

@@ -32,6 +32,11 @@ def main():
         total = torch.stack(gathered).sum(0).tolist()
         diff = {k: (v, t) for (k, v), t in zip(lib.items(), total) if v != t}
         assert lib == ref and not diff, (rank, it, diff, {k: (lib[k], ref[k]) for k in lib if lib[k] != ref[k]})
+        side = env.stats_allreduce_async(comm)            # the same collective on the library's side stream
+        env.step_random(5)                               # queued behind the snapshot, must not leak into it
+        env.stats_allreduce_wait()
+        assert side.tolist() == total, (rank, it, "side-stream all-reduce")
+        env.clear_stats()
     env.check()
     comm.close()
     if rank == 0:
