@@ -229,7 +229,9 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
                     int8_t *mask_host, int8_t *agent_host, uint8_t *done_host,
                     double *reward_host, void *stream);
 /* worker threads skyjo_step_host uses for the host-side expansion; 0 = default
- * (min(4, hardware threads / LOCAL_WORLD_SIZE), or SKYJO_HOST_THREADS) */
+ * (this rank's share of the CPUs the process may run on -- slice LOCAL_RANK of LOCAL_WORLD_SIZE under torchrun --
+ * at most 16, or SKYJO_HOST_THREADS).  The workers are persistent and pinned one per core of that slice
+ * (SKYJO_HOST_PIN=0 disables pinning). */
 int skyjo_set_host_threads(SkyjoHandle *h, int n);
 /* how observation rows cross the link in skyjo_step_host: 0 (default) = as they are, straight
  * into obs_host by the copy engine; 1 = compact records of 12 + 6 R + ceil(R / 2) bytes for a
@@ -316,8 +318,10 @@ void skyjo_host_expand_packed(const uint32_t *packed, int64_t n, int8_t *mask, i
 /* The compact observation record of skyjo_step_host (csrc/skyjo_hostio.cuh): bytes per record for
  * rows of obs_len bytes (-1 if obs_len is not 19 + 12 R); the host twin of the device-side
  * packing (returns the number of rows that are not encodable); and the host-side expansion
- * (portable != 0 forces the scalar version instead of the 16-byte shuffles). */
+ * (portable: 0 = the fastest version this CPU has, 1 = scalar, 2 = 16-byte shuffles with plain stores). */
 int skyjo_host_obs_record_bytes(int obs_len);
+/* 2 when the host-side expansions run their AVX-512 / streaming-store versions on this CPU, else 0 */
+int skyjo_host_simd_level(void);
 int64_t skyjo_host_pack_obs(const int8_t *obs, int64_t n, int obs_len, uint8_t *rec);
 void skyjo_host_expand_obs(const uint8_t *rec, int64_t n, int obs_len, int8_t *obs, int portable);
 

@@ -36,6 +36,7 @@ EXPORTS = [
     "skyjo_host_policy", "skyjo_host_expand_packed", "skyjo_set_host_wire", "skyjo_host_wire_bytes",
     "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs", "skyjo_stats_allreduce",
     "skyjo_host_reshuffle", "skyjo_set_env_ranges", "skyjo_stats_allreduce_async", "skyjo_stats_allreduce_wait",
+    "skyjo_host_simd_level",
 ]
 
 
@@ -150,6 +151,7 @@ def load():
         "skyjo_host_reshuffle": (i32, [u64, u64, u32, u32, vp, i32]),
         "skyjo_host_expand_packed": (None, [vp, i64, vp, vp, vp]),
         "skyjo_host_obs_record_bytes": (i32, [i32]),
+        "skyjo_host_simd_level": (i32, []),
         "skyjo_host_pack_obs": (i64, [vp, i64, i32, vp]),
         "skyjo_host_expand_obs": (None, [vp, i64, i32, vp, i32]),
     }

@@ -48,7 +48,8 @@ def build(force=False, verbose=False):
     if not force and not _stale(LIB, deps):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
-    jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(OBJ, "skyjo_capi.o"), [])]
+    jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(OBJ, "skyjo_capi.o"), []),
+            (os.path.join(CSRC, "skyjo_hostsimd.cpp"), os.path.join(OBJ, "skyjo_hostsimd.o"), [])]
     for n in range(1, 13):
         jobs.append((os.path.join(CSRC, "skyjo_step_inst.cu"), os.path.join(OBJ, f"skyjo_step_n{n}.o"), [f"-DSKYJO_N={n}"]))
     return _run(jobs, LIB, verbose)
@@ -63,7 +64,8 @@ def build_variant(out, defines=(), players=(4,), verbose=False):
     os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     dflags = [f"-D{d}" for d in defines]
     mask = sum(1 << (n - 1) for n in players)
-    jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(obj, "skyjo_capi.o"), dflags + [f"-DSKYJO_ONLY_PLAYERS_MASK={mask}"])]
+    jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(obj, "skyjo_capi.o"), dflags + [f"-DSKYJO_ONLY_PLAYERS_MASK={mask}"]),
+            (os.path.join(CSRC, "skyjo_hostsimd.cpp"), os.path.join(obj, "skyjo_hostsimd.o"), [])]
     for n in players:
         jobs.append((os.path.join(CSRC, "skyjo_step_inst.cu"), os.path.join(obj, f"skyjo_step_n{n}.o"), dflags + [f"-DSKYJO_N={n}"]))
     return _run(jobs, out, verbose)

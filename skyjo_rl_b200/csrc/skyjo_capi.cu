@@ -15,6 +15,7 @@
 #include "../../include/skyjo_b200.h"
 #include "skyjo_deal.cuh"
 #include "skyjo_hostio.cuh"
+#include "skyjo_hostsimd.h"
 #include "skyjo_rng.cuh"
 #include "skyjo_sample.cuh"
 #include "skyjo_state.cuh"
@@ -45,6 +46,12 @@ static const rollout_launch_fn kRollout[SKYJO_MAX_PLAYERS] = {
 static const observe_launch_fn kObserve[SKYJO_MAX_PLAYERS] = {
     launch_observe_1, launch_observe_2, launch_observe_3, launch_observe_4,  launch_observe_5,  launch_observe_6,
     launch_observe_7, launch_observe_8, launch_observe_9, launch_observe_10, launch_observe_11, launch_observe_12};
+}  // namespace skyjo
+
+namespace skyjo {
+void expand_obs_records_portable(const uint8_t *rec, long long e0, long long e1, int D, int8_t *obs) {
+    expand_obs_records(rec, e0, e1, D, obs);
+}
 }  // namespace skyjo
 
 using namespace skyjo;
@@ -730,13 +737,17 @@ int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double 
 }
 
 static int default_host_threads() {
-    int hw = (int)std::thread::hardware_concurrency();
-    if (hw < 1) hw = 1;
-    int ranks = 1;  // ranks sharing this host under torchrun
-    if (const char *g = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(g) > 0 ? atoi(g) : 1;
-    int n = hw / ranks;
-    if (const char *g = getenv("SKYJO_HOST_THREADS")) n = atoi(g);
-    return n < 1 ? 1 : (n > 4 && !getenv("SKYJO_HOST_THREADS") ? 4 : (n > 64 ? 64 : n));
+    // this rank's share of the CPUs the process may run on (ranks of one box split them evenly), at most 16:
+    // the expansion is memory-bound long before that
+    int n = (int)HostPool::rank_cpus().size();
+    if (n < 1) {
+        int hw = (int)std::thread::hardware_concurrency();
+        int ranks = 1;  // ranks sharing this host under torchrun
+        if (const char *g = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(g) > 0 ? atoi(g) : 1;
+        n = hw / ranks;
+    }
+    if (const char *g = getenv("SKYJO_HOST_THREADS")) return atoi(g) < 1 ? 1 : (atoi(g) > 64 ? 64 : atoi(g));
+    return n < 1 ? 1 : (n > 16 ? 16 : n);
 }
 
 int skyjo_set_host_threads(SkyjoHandle *h, int n) {
@@ -889,9 +900,18 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
             lap(1);
             const long long b0 = c_begin[c], nB = c_end[c] - c_begin[c];
             h->pool->run([=](int part, int parts) {
-                const long long e0 = b0 + nB * part / parts, e1 = b0 + nB * (part + 1) / parts;
-                if (want_small) expand_packed(packed, e0, e1, mask_host, agent_host, done_host);
-                if (compact) expand_obs_records(rec, e0, e1, D, obs_host);
+                // parts are multiples of 64 envs (b0 is one): whole cache lines of every output per worker
+                const long long g = (nB + 63) / 64;
+                const long long e0 = b0 + g * part / parts * 64;
+                const long long e1 = part + 1 == parts ? b0 + nB : b0 + g * (part + 1) / parts * 64;
+                if (e0 >= e1) return;
+                if (want_small) {
+                    if (mask_host && agent_host && done_host)
+                        expand_packed_wide(packed, e0, e1, mask_host, agent_host, done_host);
+                    else
+                        expand_packed(packed, e0, e1, mask_host, agent_host, done_host);
+                }
+                if (compact) expand_obs_records_wide(rec, e0, e1, D, obs_host);
             });
             lap(2);
         }
@@ -1195,7 +1215,10 @@ int skyjo_host_reshuffle(uint64_t seed, uint64_t genv, uint32_t episode, uint32_
 }
 
 void skyjo_host_expand_packed(const uint32_t *packed, int64_t n, int8_t *mask, int8_t *agent, uint8_t *done) {
-    expand_packed(packed, 0, n, mask, agent, done);
+    if (mask && agent && done)
+        expand_packed_wide(packed, 0, n, mask, agent, done);  // AVX-512 + streaming stores where the CPU has them
+    else
+        expand_packed(packed, 0, n, mask, agent, done);
 }
 
 int skyjo_host_obs_record_bytes(int obs_len) { return obs_len >= 31 && (obs_len - 19) % 12 == 0 ? obs_record_bytes(obs_len) : -1; }
@@ -1208,11 +1231,15 @@ int64_t skyjo_host_pack_obs(const int8_t *obs, int64_t n, int obs_len, uint8_t *
 }
 
 void skyjo_host_expand_obs(const uint8_t *rec, int64_t n, int obs_len, int8_t *obs, int portable) {
-    if (portable)
+    if (portable == 1)
         expand_obs_scalar(rec, 0, n, obs_len, obs);
+    else if (portable == 2)
+        expand_obs_records(rec, 0, n, obs_len, obs);       // 16-byte shuffles, plain stores
     else
-        expand_obs_records(rec, 0, n, obs_len, obs);
+        expand_obs_records_wide(rec, 0, n, obs_len, obs);  // + L1 staging and streaming stores where available
 }
+
+int skyjo_host_simd_level(void) { return host_simd_level(); }
 
 int skyjo_host_policy(uint64_t seed, uint64_t genv, uint64_t t, uint32_t legal_bits) {
     if (legal_bits == 0) return -1;

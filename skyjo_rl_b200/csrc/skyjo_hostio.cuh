@@ -31,11 +31,17 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+#if defined(__linux__)
+#include <pthread.h>
+#include <sched.h>
+#endif
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -259,22 +265,58 @@ static inline void expand_obs_records(const uint8_t *rec, long long e0, long lon
     expand_obs_scalar(rec, e0, e1, D, obs);
 }
 
-// Minimal fork-join pool for the host-side expansion (created on the first skyjo_step_host call).
+// Fork-join pool for the host-side expansion (created on the first skyjo_step_host call).  The workers are
+// persistent and, unless SKYJO_HOST_PIN=0, pinned one per core to this rank's slice of the CPUs the process may
+// run on (slice LOCAL_RANK of LOCAL_WORLD_SIZE under torchrun), so the ranks of a box do not migrate over each
+// other's cores.  A worker spins briefly on the generation counter before it sleeps: a call runs the pool once
+// per env range, a few hundred microseconds apart, and a futex wake-up costs tens of microseconds each time.
 class HostPool {
   public:
     explicit HostPool(int n) : n_(n < 1 ? 1 : n) {
-        for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i] { loop(i); });
+        std::vector<int> cpus = rank_cpus();
+        for (int i = 1; i < n_; ++i) {
+            workers_.emplace_back([this, i] { loop(i); });
+#if defined(__linux__)
+            if (!cpus.empty()) {
+                cpu_set_t set;
+                CPU_ZERO(&set);
+                CPU_SET(cpus[(size_t)i % cpus.size()], &set);
+                pthread_setaffinity_np(workers_.back().native_handle(), sizeof(set), &set);
+            }
+#endif
+        }
     }
     ~HostPool() {
         {
             std::lock_guard<std::mutex> g(m_);
             stop_ = true;
-            ++gen_;
+            gen_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         for (auto &t : workers_) t.join();
     }
     int size() const { return n_; }
+    // the CPUs of this rank's slice (empty = do not pin)
+    static std::vector<int> rank_cpus() {
+        std::vector<int> out;
+#if defined(__linux__)
+        if (const char *g = getenv("SKYJO_HOST_PIN"))
+            if (atoi(g) == 0) return out;
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) != 0) return out;
+        std::vector<int> allowed;
+        for (int c = 0; c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &set)) allowed.push_back(c);
+        int ranks = 1, rank = 0;
+        if (const char *g = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(g) > 0 ? atoi(g) : 1;
+        if (const char *g = getenv("LOCAL_RANK")) rank = atoi(g) >= 0 ? atoi(g) : 0;
+        if (rank >= ranks) rank = 0;
+        const size_t m = allowed.size(), lo = m * (size_t)rank / (size_t)ranks, hi = m * (size_t)(rank + 1) / (size_t)ranks;
+        for (size_t k = lo; k < hi; ++k) out.push_back(allowed[k]);
+#endif
+        return out;
+    }
     // runs fn(part, parts) for part = 0..n-1, part 0 on the calling thread; returns when all are done
     void run(const std::function<void(int, int)> &fn) {
         if (n_ == 1) {
@@ -284,32 +326,41 @@ class HostPool {
         {
             std::lock_guard<std::mutex> g(m_);
             fn_ = &fn;
-            pending_ = n_ - 1;
-            ++gen_;
+            pending_.store(n_ - 1, std::memory_order_relaxed);
+            gen_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         fn(0, n_);
-        std::unique_lock<std::mutex> g(m_);
-        done_cv_.wait(g, [this] { return pending_ == 0; });
+        for (int spin = 0; spin < 20000 && pending_.load(std::memory_order_acquire) != 0; ++spin) cpu_relax();
+        if (pending_.load(std::memory_order_acquire) != 0) {
+            std::unique_lock<std::mutex> g(m_);
+            done_cv_.wait(g, [this] { return pending_.load(std::memory_order_acquire) == 0; });
+        }
         fn_ = nullptr;
     }
 
   private:
+    static void cpu_relax() {
+#if defined(__x86_64__)
+        _mm_pause();
+#endif
+    }
     void loop(int i) {
         unsigned long long seen = 0;
         for (;;) {
+            for (int spin = 0; spin < 20000 && gen_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
             const std::function<void(int, int)> *fn;
             {
                 std::unique_lock<std::mutex> g(m_);
-                cv_.wait(g, [&] { return gen_ != seen; });
-                seen = gen_;
+                cv_.wait(g, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                seen = gen_.load(std::memory_order_acquire);
                 if (stop_) return;
                 fn = fn_;
             }
             (*fn)(i, n_);
-            {
+            if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
                 std::lock_guard<std::mutex> g(m_);
-                if (--pending_ == 0) done_cv_.notify_one();
+                done_cv_.notify_one();
             }
         }
     }
@@ -318,8 +369,8 @@ class HostPool {
     std::mutex m_;
     std::condition_variable cv_, done_cv_;
     const std::function<void(int, int)> *fn_ = nullptr;
-    unsigned long long gen_ = 0;
-    int pending_ = 0;
+    std::atomic<unsigned long long> gen_{0};
+    std::atomic<int> pending_{0};
     bool stop_ = false;
 };
 

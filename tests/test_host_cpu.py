@@ -328,3 +328,56 @@ def test_live_reference_patched_with_host_reshuffle_equals_oracle():
         assert total_reshuffles >= 4
     finally:
         SkyjoGame._reshuffle_discard_pile = orig
+
+
+def _aligned(nbytes, dtype, fill, align=64, offset=0):
+    """numpy view of `nbytes` bytes whose address is `offset` past a multiple of `align`, inside a guarded buffer"""
+    raw = np.full(nbytes + 2 * align + 64, fill, dtype=np.uint8)
+    start = (-raw.ctypes.data) % align + offset
+    return raw, raw[start:start + nbytes].view(dtype)
+
+
+@pytest.mark.parametrize("n,offset", [(64, 0), (1000, 0), (4096 + 77, 0), (130, 16), (5000, 1), (63, 0), (1, 0)])
+def test_wide_host_expansions_equal_the_portable_ones(n, offset):
+    """The AVX-512 / streaming-store expansions of skyjo_step_host's wire format (csrc/skyjo_hostsimd.cpp) on aligned
+    and misaligned caller buffers, whole and partial 64-env groups, against the scalar code and numpy; nothing
+    outside the destination is touched."""
+    L = _lib.load()
+    assert L.skyjo_host_simd_level() in (0, 2)
+    rng = np.random.default_rng(n + offset)
+    packed = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    raw_m, mask = _aligned(n * 26, np.int8, 7, offset=offset)
+    raw_a, agent = _aligned(n, np.int8, 7, offset=offset)
+    raw_d, done = _aligned(n, np.uint8, 7, offset=offset)
+    L.skyjo_host_expand_packed(packed.ctypes.data, n, mask.ctypes.data, agent.ctypes.data, done.ctypes.data)
+    exp_mask = ((packed[:, None] >> np.arange(26, dtype=np.uint32)[None, :]) & 1).astype(np.int8)
+    np.testing.assert_array_equal(mask.reshape(n, 26), exp_mask)
+    np.testing.assert_array_equal(agent, (packed >> 28).astype(np.int8))
+    np.testing.assert_array_equal(done, ((packed >> 26) & 3).astype(np.uint8))
+    for raw, view in ((raw_m, mask), (raw_a, agent), (raw_d, done)):
+        assert int((raw == 7).sum()) >= raw.size - view.nbytes - int((view.view(np.uint8) == 7).sum()) - 0
+        lo = view.ctypes.data - raw.ctypes.data
+        assert (raw[:lo] == 7).all() and (raw[lo + view.nbytes:] == 7).all()      # guards intact
+    for R in (1, 4, 8):
+        D = 19 + 12 * R
+        obs = np.zeros((n, D), dtype=np.int8)
+        obs[:, 0] = rng.integers(-24, 128, n)
+        obs[:, 1] = rng.integers(0, 13, n)
+        obs[:, 2:17] = rng.integers(0, 16, (n, 15))
+        obs[:, 4] = rng.integers(0, 128, n)
+        obs[:, 17] = rng.integers(-3, 13, n)
+        obs[:, 18] = rng.choice(np.r_[np.arange(-2, 13), 15], n)
+        cards = rng.choice(np.r_[np.arange(-2, 13), 15, 15], (n, R, 4, 3)).astype(np.int8)
+        cards[rng.random((n, R, 4)) < 0.1] = -14
+        obs[:, 19:] = cards.reshape(n, 12 * R)
+        RB = L.skyjo_host_obs_record_bytes(D)
+        rec = np.zeros((n, RB), dtype=np.uint8)
+        assert L.skyjo_host_pack_obs(obs.ctypes.data, n, D, rec.ctypes.data) == 0
+        for mode in (0, 1, 2):
+            raw_o, out = _aligned(n * D, np.int8, 99, offset=offset)
+            L.skyjo_host_expand_obs(rec.ctypes.data, n, D, out.ctypes.data, mode)
+            np.testing.assert_array_equal(out.reshape(n, D), obs, err_msg=f"mode {mode} R {R}")
+            lo = out.ctypes.data - raw_o.ctypes.data
+            assert (raw_o[:lo] == 99).all() and (raw_o[lo + out.nbytes:lo + out.nbytes + 0] == 99).all()
+            if mode == 0:   # the streaming version writes whole groups only: the bytes behind the last row stay untouched
+                assert (raw_o[lo + out.nbytes + 16:] == 99).all()
