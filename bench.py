@@ -584,7 +584,7 @@ def run_e2e(args, env, dev, rank, world):
     out = {"value": st["steps"] / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": B,
            "d2h_bytes_per_step": d2h, "steps": T, "ms_per_call": 1e3 * float(dt.item()) / T,
            "host_buffer_bytes_filled_per_step": B * (D + 26 + 1 + 1 + 8 * N),
-           "wire_bytes_per_env": round(e.host_wire_bytes / float(B), 2),
+           "wire_bytes_per_env": round(e.host_wire_bytes / float(B), 2), "compact_ranges_of_8": e.host_wire_share,
            "api": "skyjo_step_host (C ABI) via BatchedSkyjoEnv.step_host, pinned host buffers: obs int8[B,D], "
                   "mask int8[B,26], agent, done, reward f64[B,N] all filled every step; one call = one env-step of "
                   "every env (wall clock around the calls, max over ranks)"}

@@ -230,18 +230,21 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
                     double *reward_host, void *stream);
 /* worker threads skyjo_step_host uses for the host-side expansion; 0 = default
  * (this rank's share of the CPUs the process may run on -- slice LOCAL_RANK of LOCAL_WORLD_SIZE under torchrun --
- * at most 16, or SKYJO_HOST_THREADS).  The workers are persistent and pinned one per core of that slice
+ * minus one, between 2 and 8, or SKYJO_HOST_THREADS).  The workers are persistent and pinned one per core of that slice
  * (SKYJO_HOST_PIN=0 disables pinning). */
 int skyjo_set_host_threads(SkyjoHandle *h, int n);
-/* how observation rows cross the link in skyjo_step_host: 0 (default) = as they are, straight
- * into obs_host by the copy engine; 1 = compact records of 12 + 6 R + ceil(R / 2) bytes for a
- * row of 19 + 12 R bytes, packed on the device and expanded on the host by the worker threads
- * (env SKYJO_HOST_WIRE=compact selects 1 at creation).  Mode 1 moves 1.7x fewer bytes but pays
- * for it in host memory traffic: it only wins where the link, not the host, is the bottleneck
- * (on the B200 box of this round, 16 host threads: 5.4e8 vs 7.3e8 env-steps/s -- DESIGN.md). */
+/* how observation rows cross the link in skyjo_step_host, per env range of the batch: 0 = as they are, straight
+ * into obs_host by the copy engine (no CPU work); 1 = compact records of 12 + 6 R + ceil(R / 2) bytes for a row of
+ * 19 + 12 R bytes, packed on the device and expanded on the host by the worker threads (1.7x fewer bytes on the
+ * link, paid for in host memory traffic); 2 = mixed: the first k of 8 ranges compact, the rest raw, k tuned between
+ * calls by measurement (perturb and observe on the call time, starting from k = 0).  Default: 2 where the CPU has the
+ * AVX-512 streaming expansions (skyjo_host_simd_level() == 2), else 0; env SKYJO_HOST_WIRE=raw|compact|mixed
+ * selects at creation, SKYJO_HOST_MIX=k pins the share.  All modes fill the host buffers bit-identically. */
 int skyjo_set_host_wire(SkyjoHandle *h, int mode);
 /* bytes the last skyjo_step_host call moved device -> host */
 int64_t skyjo_host_wire_bytes(const SkyjoHandle *h);
+/* of 8 env ranges, how many the next skyjo_step_host call sends as compact records (0 raw .. 8 compact) */
+int skyjo_host_wire_share(const SkyjoHandle *h);
 
 /* SimpleSkyjoEnv.observe(agent) (skyjo_env.py:199-214) for an arbitrary seat; agent = -1
  * means each env's agent_selection.  Writes int8[B,D] / int8[B,26]. */
@@ -318,9 +321,11 @@ void skyjo_host_expand_packed(const uint32_t *packed, int64_t n, int8_t *mask, i
 /* The compact observation record of skyjo_step_host (csrc/skyjo_hostio.cuh): bytes per record for
  * rows of obs_len bytes (-1 if obs_len is not 19 + 12 R); the host twin of the device-side
  * packing (returns the number of rows that are not encodable); and the host-side expansion
- * (portable: 0 = the fastest version this CPU has, 1 = scalar, 2 = 16-byte shuffles with plain stores). */
+ * (portable: 0 = the fastest version this CPU has -- `rec` must then be readable 256 bytes past its end --, 1 = scalar,
+ * 2 = 16-byte shuffles with plain stores, 3 = those staged in L1 and streamed out). */
 int skyjo_host_obs_record_bytes(int obs_len);
-/* 2 when the host-side expansions run their AVX-512 / streaming-store versions on this CPU, else 0 */
+/* 2 when the host-side expansions run their AVX-512 / streaming-store versions on this CPU, 3 with AVX-512 VBMI
+ * (record expansion by byte gathers), else 0 */
 int skyjo_host_simd_level(void);
 int64_t skyjo_host_pack_obs(const int8_t *obs, int64_t n, int obs_len, uint8_t *rec);
 void skyjo_host_expand_obs(const uint8_t *rec, int64_t n, int obs_len, int8_t *obs, int portable);

@@ -36,7 +36,7 @@ EXPORTS = [
     "skyjo_host_policy", "skyjo_host_expand_packed", "skyjo_set_host_wire", "skyjo_host_wire_bytes",
     "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs", "skyjo_stats_allreduce",
     "skyjo_host_reshuffle", "skyjo_set_env_ranges", "skyjo_stats_allreduce_async", "skyjo_stats_allreduce_wait",
-    "skyjo_host_simd_level",
+    "skyjo_host_simd_level", "skyjo_host_wire_share",
 ]
 
 
@@ -130,6 +130,7 @@ def load():
         "skyjo_set_host_threads": (i32, [vp, i32]),
         "skyjo_set_host_wire": (i32, [vp, i32]),
         "skyjo_host_wire_bytes": (i64, [vp]),
+        "skyjo_host_wire_share": (i32, [vp]),
         "skyjo_observe": (i32, [vp, i32, vp, vp, vp]),
         "skyjo_stats_device": (i32, [vp, vp, vp]),
         "skyjo_stats_host": (i32, [vp, vp, vp]),

@@ -114,7 +114,12 @@ struct SkyjoHandle {
     unsigned int *counter_dev, *counter_host;   // [2]: finished envs of the call, "row not encodable" flag
     uint8_t *rec_dev, *rec_host;            // compact observation records, [B][obs_record_bytes(D)]
     cudaEvent_t ev_rec_done[HOSTIO_MAX_CHUNKS];
-    int wire_mode;                          // 0 raw rows (default), 1 compact records
+    int wire_mode;                          // 0 raw rows, 1 compact records, 2 mixed (adaptive share of the env ranges)
+    // mixed mode: mix_k of 8 env ranges travel as compact records.  The share is tuned by measurement: the mean
+    // call time of every window of 6 calls is filed under its k; the next window runs at the untried neighbour of
+    // the fastest k seen, or stays there for mix_hold windows once both neighbours are known to be slower.
+    int mix_k, mix_calls, mix_hold;
+    double mix_acc_us, mix_t[9];
     long long last_d2h_bytes;               // bytes queued device -> host by the last skyjo_step_host
     double *entries_host, *entries_dev;     // host-mapped pinned, [cap][1 + N]
     unsigned int sparse_cap;
@@ -271,8 +276,16 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     h->hostio_ready = false;
     h->pool = nullptr;
     h->host_threads = 0;
-    h->wire_mode = 0;
-    if (const char *g = getenv("SKYJO_HOST_WIRE")) h->wire_mode = (atoi(g) == 1 || !strcmp(g, "compact")) ? 1 : 0;
+    // default: mixed where the CPU has the streaming expansions (csrc/skyjo_hostsimd.cpp), else raw rows
+    h->wire_mode = host_simd_level() >= 2 ? 2 : 0;
+    if (const char *g = getenv("SKYJO_HOST_WIRE"))
+        h->wire_mode = (atoi(g) == 1 || !strcmp(g, "compact")) ? 1 : ((atoi(g) == 2 || !strcmp(g, "mixed")) ? 2 : 0);
+    h->mix_k = 0;
+    if (const char *g = getenv("SKYJO_HOST_MIX")) h->mix_k = atoi(g);   // experiment knob: fixes the share
+    h->mix_calls = -1;  // the first call allocates: not timed
+    h->mix_hold = 0;
+    h->mix_acc_us = 0.0;
+    for (double &v : h->mix_t) v = -1.0;
     h->last_d2h_bytes = 0;
     h->rec_dev = h->rec_host = nullptr;
     h->last_reward_host = nullptr;
@@ -747,7 +760,8 @@ static int default_host_threads() {
         n = hw / ranks;
     }
     if (const char *g = getenv("SKYJO_HOST_THREADS")) return atoi(g) < 1 ? 1 : (atoi(g) > 64 ? 64 : atoi(g));
-    return n < 1 ? 1 : (n > 16 ? 16 : n);
+    n -= 1;  // one core of the slice stays free for the caller's other threads (CUDA's, the interpreter's)
+    return n < 2 ? 2 : (n > 8 ? 8 : n);
 }
 
 int skyjo_set_host_threads(SkyjoHandle *h, int n) {
@@ -793,6 +807,7 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     const size_t B = (size_t)h->B, N = (size_t)h->cfg.num_players;
     using clk = std::chrono::steady_clock;
     auto t_prev = clk::now();
+    const auto t_call0 = t_prev;
     auto lap = [&](int k) {
         const auto now = clk::now();
         h->trace_us[k] += std::chrono::duration<double, std::micro>(now - t_prev).count();
@@ -803,15 +818,9 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     rc = quiesce(h, s);
     if (rc) return rc;
     const bool want_small = mask_host || agent_host || done_host || reward_host;
-    const bool compact = obs_host && h->wire_mode == 1;
     const int RB = obs_record_bytes(h->obs_len);
-    if (compact && !h->rec_dev) {  // record staging of the opt-in wire mode, on its first use
-        CU(cudaMalloc(&h->rec_dev, B * (size_t)RB));
-        CU(cudaHostAlloc(&h->rec_host, B * (size_t)RB, cudaHostAllocDefault));
-    }
-    if (want_small || compact) CU(cudaMemsetAsync(h->counter_dev, 0, 8, s));
     // env ranges: multiples of ENV_PAD envs, so every range starts on a tile and on a 16-byte boundary
-    int chunks = h->B >= (1 << 18) ? (compact ? 8 : 4) : (h->B >= (1 << 16) ? 2 : 1);
+    int chunks = h->B >= (1 << 18) ? ((obs_host && h->wire_mode != 0) ? 8 : 4) : (h->B >= (1 << 16) ? 2 : 1);
     if (const char *g = getenv("SKYJO_HOST_CHUNKS")) chunks = atoi(g);
     if (chunks < 1) chunks = 1;
     if (chunks > HOSTIO_MAX_CHUNKS) chunks = HOSTIO_MAX_CHUNKS;
@@ -823,11 +832,27 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
         c_end[nc] = b + per < h->B ? b + per : h->B;
         ++nc;
     }
+    // Per range, the observation rows travel raw (the copy engine writes them into obs_host, no CPU work) or as
+    // compact records (1.7x fewer bytes on the link, expanded by the workers).  Mixed mode sends the first
+    // n_compact ranges compact -- their expansion then overlaps the raw copies of the later ranges -- and moves
+    // the share towards the faster call time (perturb and observe: what limits the call -- the link, or the host's
+    // memory system that the copy engine and the workers share -- differs from box to box).
+    const bool adapt = h->wire_mode == 2 && !getenv("SKYJO_HOST_MIX");
+    int n_compact = !obs_host ? 0 : (h->wire_mode == 1 ? nc : (h->wire_mode == 2 ? (h->mix_k * nc + 4) / 8 : 0));
+    if (n_compact > nc) n_compact = nc;
+    if (n_compact < 0) n_compact = 0;
+    const bool any_compact = n_compact > 0;
+    if (obs_host && h->wire_mode != 0 && !h->rec_dev) {  // record staging, in the first call that may need it later
+        CU(cudaMalloc(&h->rec_dev, B * (size_t)RB));
+        CU(cudaHostAlloc(&h->rec_host, B * (size_t)RB + 256, cudaHostAllocDefault));  // + the gather windows' over-read
+    }
+    if (want_small || any_compact) CU(cudaMemsetAsync(h->counter_dev, 0, 8, s));
     StepParams p = make_params(h);
     p.actions = act_dev;
     p.action_dtype = SKYJO_ACT_U8;
     long long d2h = 0;
     for (int c = 0; c < nc; ++c) {
+        const bool compact = c < n_compact;
         const size_t e0 = (size_t)c_begin[c], n = (size_t)(c_end[c] - c_begin[c]);
         CU(cudaMemcpyAsync(act_dev + e0, actions_host + e0, n, cudaMemcpyHostToDevice, s));
         p.tile_off = c_begin[c] / TILE;
@@ -867,7 +892,7 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
         }
     }
     h->t += 1;
-    if (reward_host || compact) {
+    if (reward_host || any_compact) {
         CU(cudaMemcpyAsync(h->counter_host, h->counter_dev, 8, cudaMemcpyDeviceToHost, cs));
         CU(cudaEventRecord(h->ev_counter_done, cs));
         d2h += 8;
@@ -890,11 +915,13 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
         }
         h->last_reward_rows.clear();
     }
-    if (want_small || compact) {
+    if (want_small || any_compact) {
         const uint32_t *packed = h->packed_host;
         const uint8_t *rec = h->rec_host;
         const int D = h->obs_len;
         for (int c = 0; c < nc; ++c) {
+            const bool compact = c < n_compact;
+            if (!want_small && !compact) continue;
             // the record copy of a chunk is queued behind its packed words: one wait covers both
             CU(cudaEventSynchronize(compact ? h->ev_rec_done[c] : h->ev_small_done[c]));
             lap(1);
@@ -911,11 +938,11 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
                     else
                         expand_packed(packed, e0, e1, mask_host, agent_host, done_host);
                 }
-                if (compact) expand_obs_records_wide(rec, e0, e1, D, obs_host);
+                if (compact) expand_obs_records_wide(rec, e0, e1, D, obs_host, 256);
             });
             lap(2);
         }
-        if (reward_host || compact) CU(cudaEventSynchronize(h->ev_counter_done));
+        if (reward_host || any_compact) CU(cudaEventSynchronize(h->ev_counter_done));
         if (reward_host) {
             const unsigned int cnt = h->counter_host[0];
             if (cnt <= h->sparse_cap) {
@@ -934,7 +961,7 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
                 h->last_reward_host = nullptr;  // every row may be non-zero: start from a memset next time
             }
         }
-        if (compact && h->counter_host[1] != 0u) {
+        if (any_compact && h->counter_host[1] != 0u) {
             // a row outside the record's symbol sets (not reachable from the 4-bit-bin state layout): dense copy
             CU(cudaMemcpyAsync(obs_host, h->outs.obs_dev, B * (size_t)D, cudaMemcpyDeviceToHost, cs));
             CU(cudaEventRecord(h->ev_all_done, cs));
@@ -946,16 +973,44 @@ int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_hos
     lap(4);
     h->trace_calls += 1;
     h->last_d2h_bytes = d2h;
+    if (adapt && obs_host && nc >= 4) {
+        if (h->mix_calls >= 0) h->mix_acc_us += std::chrono::duration<double, std::micro>(clk::now() - t_call0).count();
+        if (++h->mix_calls >= 6) {
+            const double t = h->mix_acc_us / h->mix_calls;
+            int k = h->mix_k < 0 ? 0 : (h->mix_k > 8 ? 8 : h->mix_k);
+            h->mix_t[k] = h->mix_t[k] < 0.0 ? t : 0.5 * (h->mix_t[k] + t);
+            if (h->mix_hold > 0) {
+                if (--h->mix_hold == 0)  // look around again: the neighbours' figures are stale
+                    for (int q = 0; q <= 8; ++q)
+                        if (q != k) h->mix_t[q] = -1.0;
+            } else {
+                int best = k;
+                for (int q = 0; q <= 8; ++q)
+                    if (h->mix_t[q] >= 0.0 && h->mix_t[q] < h->mix_t[best]) best = q;
+                if (best > 0 && h->mix_t[best - 1] < 0.0) k = best - 1;
+                else if (best < 8 && h->mix_t[best + 1] < 0.0) k = best + 1;
+                else {
+                    k = best;
+                    h->mix_hold = 40;
+                }
+                h->mix_k = k;
+            }
+            h->mix_calls = 0;
+            h->mix_acc_us = 0.0;
+        }
+    }
     return SKYJO_OK;
 }
 
 int skyjo_set_host_wire(SkyjoHandle *h, int mode) {
-    if (!h || (mode != 0 && mode != 1)) return fail(SKYJO_E_INVALID, "wire mode must be 0 (raw rows) or 1 (compact records)");
+    if (!h || mode < 0 || mode > 2)
+        return fail(SKYJO_E_INVALID, "wire mode must be 0 (raw rows), 1 (compact records) or 2 (mixed, adaptive)");
     h->wire_mode = mode;
     return SKYJO_OK;
 }
 
 int64_t skyjo_host_wire_bytes(const SkyjoHandle *h) { return h ? h->last_d2h_bytes : -1; }
+int skyjo_host_wire_share(const SkyjoHandle *h) { return h ? (h->wire_mode == 1 ? 8 : (h->wire_mode == 2 ? h->mix_k : 0)) : -1; }
 
 int skyjo_observe(SkyjoHandle *h, int agent, void *obs_dev, void *mask_dev, void *stream) {
     if (!h || !obs_dev || !mask_dev) return fail(SKYJO_E_INVALID, "null argument");
@@ -1235,8 +1290,11 @@ void skyjo_host_expand_obs(const uint8_t *rec, int64_t n, int obs_len, int8_t *o
         expand_obs_scalar(rec, 0, n, obs_len, obs);
     else if (portable == 2)
         expand_obs_records(rec, 0, n, obs_len, obs);       // 16-byte shuffles, plain stores
+    else if (portable == 3)
+        expand_obs_records_wide(rec, 0, n, obs_len, obs, 0);    // L1 staging + streaming stores where available
     else
-        expand_obs_records_wide(rec, 0, n, obs_len, obs);  // + L1 staging and streaming stores where available
+        // + VBMI byte gathers where available; `rec` must then be readable 256 bytes past its end
+        expand_obs_records_wide(rec, 0, n, obs_len, obs, 256);
 }
 
 int skyjo_host_simd_level(void) { return host_simd_level(); }

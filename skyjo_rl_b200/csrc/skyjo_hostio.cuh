@@ -273,6 +273,7 @@ static inline void expand_obs_records(const uint8_t *rec, long long e0, long lon
 class HostPool {
   public:
     explicit HostPool(int n) : n_(n < 1 ? 1 : n) {
+        if (const char *g = getenv("SKYJO_HOST_SPIN")) spin_ = atoi(g) < 0 ? 0 : atoi(g);  // experiment knob
         std::vector<int> cpus = rank_cpus();
         for (int i = 1; i < n_; ++i) {
             workers_.emplace_back([this, i] { loop(i); });
@@ -331,7 +332,7 @@ class HostPool {
         }
         cv_.notify_all();
         fn(0, n_);
-        for (int spin = 0; spin < 20000 && pending_.load(std::memory_order_acquire) != 0; ++spin) cpu_relax();
+        for (int spin = 0; spin < 3 * spin_ && pending_.load(std::memory_order_acquire) != 0; ++spin) cpu_relax();
         if (pending_.load(std::memory_order_acquire) != 0) {
             std::unique_lock<std::mutex> g(m_);
             done_cv_.wait(g, [this] { return pending_.load(std::memory_order_acquire) == 0; });
@@ -348,7 +349,7 @@ class HostPool {
     void loop(int i) {
         unsigned long long seen = 0;
         for (;;) {
-            for (int spin = 0; spin < 20000 && gen_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
+            for (int spin = 0; spin < spin_ && gen_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
             const std::function<void(int, int)> *fn;
             {
                 std::unique_lock<std::mutex> g(m_);
@@ -365,6 +366,7 @@ class HostPool {
         }
     }
     int n_;
+    int spin_ = 1500;  // pause iterations (~100 us) a worker polls before it sleeps
     std::vector<std::thread> workers_;
     std::mutex m_;
     std::condition_variable cv_, done_cv_;

@@ -7,7 +7,11 @@
 // rows costs five instructions and goes out with a streaming store.
 #include "skyjo_hostsimd.h"
 
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
+#include <vector>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -15,6 +19,23 @@
 namespace skyjo {
 
 constexpr int PACK_DONE_SH = 26, PACK_AGENT_SH = 28;
+
+static bool mask_streaming_stores() {
+    static const bool nt = [] {
+        const char *g = getenv("SKYJO_HOST_NT_MASK");  // experiment knob
+        return g && atoi(g) != 0;
+    }();
+    return nt;
+}
+
+// SKYJO_HOST_NT=0 (experiment knob): plain 64-byte stores instead of streaming ones for the record expansion
+static bool use_streaming_stores() {
+    static const bool nt = [] {
+        const char *g = getenv("SKYJO_HOST_NT");
+        return !(g && atoi(g) == 0);
+    }();
+    return nt;
+}
 
 // ---- portable ---------------------------------------------------------------------------------
 static inline uint64_t spread8(uint32_t b) {
@@ -64,6 +85,10 @@ struct MaskTables {
 __attribute__((target("avx512f,avx512bw,avx512vl"))) static void expand_packed_avx512(
     const uint32_t *packed, long long e0, long long groups, int8_t *mask, int8_t *agent, uint8_t *done) {
     static const MaskTables T;
+    // plain stores: measured on the B200 boxes, streaming the mask rows while the copy engine writes the observation
+    // rows into the same host memory slows the copies down (raw wire, 4 workers: 5.3-5.8e8 env-steps/s streamed
+    // against 7.3e8 plain)
+    const bool nt = mask_streaming_stores();
     alignas(64) uint32_t local[64 + 16];
     for (long long g = 0; g < groups; ++g) {
         const uint32_t *src = packed + e0 + 64 * g;
@@ -82,7 +107,10 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) static void expand_packed_a
                 const __m512i bytes = _mm512_shuffle_epi8(_mm512_broadcast_i32x4(win),
                                                           _mm512_load_si512(T.idx[L]));
                 const __mmask64 k = _mm512_test_epi8_mask(bytes, _mm512_load_si512(T.sel[L]));
-                _mm512_stream_si512(reinterpret_cast<__m512i *>(dst + 64 * L), _mm512_maskz_set1_epi8(k, 1));
+                if (nt)
+                    _mm512_stream_si512(reinterpret_cast<__m512i *>(dst + 64 * L), _mm512_maskz_set1_epi8(k, 1));
+                else
+                    _mm512_store_si512(reinterpret_cast<__m512i *>(dst + 64 * L), _mm512_maskz_set1_epi8(k, 1));
             }
         }
         __m512i ag = _mm512_setzero_si512(), dn = _mm512_setzero_si512();
@@ -95,8 +123,13 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) static void expand_packed_a
         dn = _mm512_inserti32x4(dn, _mm512_cvtepi32_epi8(_mm512_and_si512(_mm512_srli_epi32(w[1], PACK_DONE_SH), three)), 1);
         dn = _mm512_inserti32x4(dn, _mm512_cvtepi32_epi8(_mm512_and_si512(_mm512_srli_epi32(w[2], PACK_DONE_SH), three)), 2);
         dn = _mm512_inserti32x4(dn, _mm512_cvtepi32_epi8(_mm512_and_si512(_mm512_srli_epi32(w[3], PACK_DONE_SH), three)), 3);
-        _mm512_stream_si512(reinterpret_cast<__m512i *>(agent + e0 + 64 * g), ag);
-        _mm512_stream_si512(reinterpret_cast<__m512i *>(done + e0 + 64 * g), dn);
+        if (nt) {
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(agent + e0 + 64 * g), ag);
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(done + e0 + 64 * g), dn);
+        } else {
+            _mm512_store_si512(reinterpret_cast<__m512i *>(agent + e0 + 64 * g), ag);
+            _mm512_store_si512(reinterpret_cast<__m512i *>(done + e0 + 64 * g), dn);
+        }
     }
     _mm_sfence();
 }
@@ -158,13 +191,139 @@ __attribute__((target("avx512f,avx512bw,avx512vl,ssse3"))) static void expand_ob
     }
     _mm_sfence();
 }
+
+// ---- AVX-512 VBMI: one output line per ~15 instructions, no staging ----------------------------------------
+// The rows of 64 consecutive envs are 64 D bytes = D output lines.  Output byte b of the group belongs to row
+// b / D, position j = b % D, and is a function of ONE byte of that env's record (csrc/skyjo_hostio.cuh has the
+// record layout): a raw byte (j = 0, and the value-0 bin j = 4), or one of its nibbles taken as is (j = 1, the
+// other bins), minus 3 (the discard top, j = 17) or through the card table (the hand j = 18 and the slots j >= 19;
+// 15 stays 15 = hidden); a slot whose column is removed shows -14, which is one bit of the record's flag bytes.
+// Per line the tables hold, for each of the 64 bytes, where its source byte and its flag byte sit inside two
+// 128-byte windows of the group's records, which nibble, which value table, and the flag bit.  vpermt2b gathers,
+// a 64-entry vpermb is the value table.
+struct ObsLineTables {
+    int D = 0, RB = 0;
+    bool ok = false;
+    std::vector<int> woff, foff;               // per line: byte offset of the two windows from the group's first record
+    std::vector<uint8_t> sb, sbf, kind, fsel;  // per line x 64
+    std::vector<uint64_t> k_hi, k_raw;         // per line: high-nibble positions, raw-byte positions
+};
+
+static void build_obs_tables(ObsLineTables &T, int D) {
+    const int R = (D - 19) / 12, RB = 12 + 6 * R + (R + 1) / 2;
+    T.D = D;
+    T.RB = RB;
+    T.ok = true;
+    T.woff.assign(D, 0);
+    T.foff.assign(D, 0);
+    T.sb.assign((size_t)D * 64, 0);
+    T.sbf.assign((size_t)D * 64, 0);
+    T.kind.assign((size_t)D * 64, 0);
+    T.fsel.assign((size_t)D * 64, 0);
+    T.k_hi.assign(D, 0);
+    T.k_raw.assign(D, 0);
+    for (int L = 0; L < D; ++L) {
+        int src[64], fsrc[64];
+        int lo = 1 << 30, hi = -1, flo = 1 << 30, fhi = -1;
+        for (int x = 0; x < 64; ++x) {
+            const int b = 64 * L + x, row = b / D, j = b % D, base = row * RB;
+            int byte = 0, nib_hi = 0, kind = 0, raw = 0, fb = -1, fbit = 0;  // kind: 0 as is, 1 minus 3, 2 card table
+            if (j == 0) {
+                byte = 0; raw = 1;
+            } else if (j == 1) {
+                byte = 1;
+            } else if (j == 4) {
+                byte = 3; raw = 1;
+            } else if (j <= 16) {
+                const int k = j - 2;
+                byte = 4 + (k >> 1); nib_hi = k & 1;
+            } else if (j == 17) {
+                byte = 1; nib_hi = 1; kind = 1;
+            } else if (j == 18) {
+                byte = 2; kind = 2;
+            } else {
+                const int i = j - 19, q = i / 12, col = (i % 12) / 3;
+                byte = 12 + (i >> 1); nib_hi = i & 1; kind = 2;
+                fb = 12 + 6 * R + (q >> 1); fbit = 4 * (q & 1) + col;
+            }
+            src[x] = base + byte;
+            fsrc[x] = fb < 0 ? -1 : base + fb;
+            lo = src[x] < lo ? src[x] : lo;
+            hi = src[x] > hi ? src[x] : hi;
+            if (fb >= 0) {
+                flo = fsrc[x] < flo ? fsrc[x] : flo;
+                fhi = fsrc[x] > fhi ? fsrc[x] : fhi;
+            }
+            T.kind[(size_t)L * 64 + x] = (uint8_t)(16 * kind);
+            T.fsel[(size_t)L * 64 + x] = (uint8_t)(fb < 0 ? 0 : (1 << fbit));
+            if (nib_hi) T.k_hi[L] |= 1ull << x;
+            if (raw) T.k_raw[L] |= 1ull << x;
+        }
+        if (fhi < 0) flo = fhi = lo;
+        if (hi - lo >= 128 || fhi - flo >= 128) T.ok = false;
+        T.woff[L] = lo;
+        T.foff[L] = flo;
+        for (int x = 0; x < 64; ++x) {
+            T.sb[(size_t)L * 64 + x] = (uint8_t)((src[x] - lo) & 127);
+            T.sbf[(size_t)L * 64 + x] = (uint8_t)(fsrc[x] < 0 ? 0 : ((fsrc[x] - flo) & 127));
+        }
+    }
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi"))) static void expand_obs_vbmi(
+    const ObsLineTables &T, const uint8_t *rec, long long e0, long long groups, int8_t *obs) {
+    const int D = T.D, RB = T.RB;
+    alignas(64) int8_t vt[64];  // value tables: [0..15] as is, [16..31] minus 3, [32..47] cards (value + 2 -> value, 15 hidden)
+    for (int i = 0; i < 16; ++i) {
+        vt[i] = (int8_t)i;
+        vt[16 + i] = (int8_t)(i - 3);
+        vt[32 + i] = (int8_t)(i == 15 ? 15 : i - 2);
+        vt[48 + i] = 0;
+    }
+    const bool nt = use_streaming_stores();
+    const __m512i table = _mm512_load_si512(vt), low4 = _mm512_set1_epi8(0x0F), removed = _mm512_set1_epi8(-14);
+    for (long long g = 0; g < groups; ++g) {
+        const uint8_t *base = rec + (e0 + 64 * g) * RB;
+        int8_t *dst = obs + (e0 + 64 * g) * D;
+        for (int L = 0; L < D; ++L) {
+            const uint8_t *w = base + T.woff[L], *f = base + T.foff[L];
+            const __m512i t = _mm512_permutex2var_epi8(_mm512_loadu_si512(w), _mm512_loadu_si512(T.sb.data() + (size_t)L * 64),
+                                                       _mm512_loadu_si512(w + 64));
+            const __m512i n = _mm512_mask_blend_epi8(T.k_hi[L], _mm512_and_si512(t, low4),
+                                                     _mm512_and_si512(_mm512_srli_epi16(t, 4), low4));
+            __m512i v = _mm512_permutexvar_epi8(_mm512_or_si512(n, _mm512_loadu_si512(T.kind.data() + (size_t)L * 64)), table);
+            v = _mm512_mask_blend_epi8(T.k_raw[L], v, t);
+            const __m512i fl = _mm512_permutex2var_epi8(_mm512_loadu_si512(f), _mm512_loadu_si512(T.sbf.data() + (size_t)L * 64),
+                                                        _mm512_loadu_si512(f + 64));
+            const __mmask64 k = _mm512_test_epi8_mask(fl, _mm512_loadu_si512(T.fsel.data() + (size_t)L * 64));
+            v = _mm512_mask_blend_epi8(k, v, removed);
+            if (nt)
+                _mm512_stream_si512(reinterpret_cast<__m512i *>(dst + 64 * L), v);
+            else
+                _mm512_store_si512(reinterpret_cast<__m512i *>(dst + 64 * L), v);
+        }
+    }
+    _mm_sfence();
+}
+
+static const ObsLineTables *obs_tables_for(int D) {
+    // one table set per row length (13 possible: D = 19 + 12 R), built on first use
+    static ObsLineTables tables[13];
+    static std::mutex m;
+    const int R = (D - 19) / 12;
+    if (R < 1 || R > 12 || D != 19 + 12 * R) return nullptr;
+    std::lock_guard<std::mutex> g(m);
+    if (tables[R].D != D) build_obs_tables(tables[R], D);
+    return tables[R].ok ? &tables[R] : nullptr;
+}
 #endif
 
 // ---- dispatch ------------------------------------------------------------------------------------
 int host_simd_level() {
 #if defined(__x86_64__)
     static const int level = (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
-                              __builtin_cpu_supports("avx512vl")) ? 2 : 0;
+                              __builtin_cpu_supports("avx512vl"))
+                                 ? (__builtin_cpu_supports("avx512vbmi") ? 3 : 2) : 0;
     return level;
 #else
     return 0;
@@ -190,7 +349,7 @@ void expand_packed_wide(const uint32_t *packed, long long e0, long long e1, int8
 // portable record expansion lives in skyjo_hostio.cuh (expand_obs_records); declared here for the fallback
 void expand_obs_records_portable(const uint8_t *rec, long long e0, long long e1, int D, int8_t *obs);
 
-void expand_obs_records_wide(const uint8_t *rec, long long e0, long long e1, int D, int8_t *obs) {
+void expand_obs_records_wide(const uint8_t *rec, long long e0, long long e1, int D, int8_t *obs, long long rec_slack) {
 #if defined(__x86_64__)
     if (host_simd_level() >= 2 && ((uintptr_t)obs & 63) == 0) {
         const int R = (D - 19) / 12, RB = 12 + 6 * R + (R + 1) / 2;
@@ -198,7 +357,13 @@ void expand_obs_records_wide(const uint8_t *rec, long long e0, long long e1, int
         if (a0 < e1) {
             const long long groups = (e1 - a0) / 64;
             expand_obs_records_portable(rec, e0, a0, D, obs);
-            expand_obs_avx512(rec, a0, groups, D, RB, obs);
+            // the gathers read 128-byte windows of the record array: the last group of the whole array may not
+            // (the caller's array ends there), so it takes the staged version
+            const ObsLineTables *T = host_simd_level() >= 3 && rec_slack >= 256 ? obs_tables_for(D) : nullptr;
+            if (T)
+                expand_obs_vbmi(*T, rec, a0, groups, obs);
+            else
+                expand_obs_avx512(rec, a0, groups, D, RB, obs);
             expand_obs_records_portable(rec, a0 + 64 * groups, e1, D, obs);
             return;
         }

@@ -290,14 +290,20 @@ class BatchedSkyjoEnv:
         _lib.check(self._L.skyjo_set_host_threads(self._h, int(n)))
 
     def set_host_wire(self, mode="raw"):
-        """How step_host moves observation rows over the link: "raw" rows (default) or "compact" records, packed
-        on the device and expanded on the host (csrc/skyjo_hostio.cuh)."""
-        _lib.check(self._L.skyjo_set_host_wire(self._h, {"raw": 0, "compact": 1}[mode]))
+        """How step_host moves observation rows over the link: "raw" rows, "compact" records (packed on the device,
+        expanded on the host) or "mixed" (an adaptive share of the env ranges compact; the default where the CPU
+        has AVX-512) -- csrc/skyjo_hostio.cuh."""
+        _lib.check(self._L.skyjo_set_host_wire(self._h, {"raw": 0, "compact": 1, "mixed": 2}[mode]))
 
     @property
     def host_wire_bytes(self):
         """bytes the last step_host call moved device -> host"""
         return int(self._L.skyjo_host_wire_bytes(self._h))
+
+    @property
+    def host_wire_share(self):
+        """of 8 env ranges, how many step_host currently sends as compact records"""
+        return int(self._L.skyjo_host_wire_share(self._h))
 
     def observe(self, agent=None):
         """SimpleSkyjoEnv.observe (skyjo_env.py:199-214).  agent=None returns the live buffers
