@@ -538,14 +538,23 @@ int skyjo_seed(SkyjoHandle *h, uint64_t seed, void *stream) {
     return skyjo_reset(h, stream);
 }
 
-// Refill cadence of the pre-dealt "next" episodes.  With the in-kernel legal policy no env can
-// finish twice within 8 steps (an episode lasts >= 21 act() calls), so one flagged deal launch
-// per 8 steps suffices; external actions may be illegal and end an episode at once, so deal
-// after every step.
+// Refill cadence of the pre-dealt "next" episodes: the window length P in steps.  The deal D_w of the envs that
+// finished in window w has to be complete before any of them can finish AGAIN, and it is only awaited when window
+// w + 2 opens, so 2 P must not exceed the shortest possible episode.  Under legal play (the in-kernel policy) a
+// seat uncovers at most one of its ten hidden cards per turn (skyjo.py:389-404) and the game ends at the draw
+// action of a seat with none left (:350-356): the starter needs 9 N + 1 turns of two act() calls, the other N - 1
+// seats then play once more, and the terminating draw call follows -- 20 N + 1 act() calls at least (21 for one
+// player, 81 for four).  P = the largest multiple of 8 below half of that, at most 32: 8 / 16 / 24 / 32 steps for
+// N = 1 / 2 / 3 / >= 4.  Longer windows mean fewer, fuller flagged deal launches (a deal CTA compacts the hits of
+// 1024 envs: 61 decks per CTA at P = 8 and N = 4, i.e. two warps; 240 at P = 32).  A step cap shortens episodes;
+// external actions may be illegal and end an episode at once, so they deal after every step.
 static int deal_period(const SkyjoHandle *h, bool policy) {
     if (!policy) return 1;
-    if (h->cfg.max_episode_steps > 0 && h->cfg.max_episode_steps < 16) return 1;
-    return 8;
+    int shortest = 20 * h->cfg.num_players + 1;
+    if (h->cfg.max_episode_steps > 0 && h->cfg.max_episode_steps < shortest) shortest = h->cfg.max_episode_steps;
+    int p = shortest / 2 / 8 * 8;
+    if (const char *g = getenv("SKYJO_DEAL_PERIOD")) p = atoi(g) < p ? atoi(g) : p;  // experiment knob (may only shorten)
+    return p < 8 ? 1 : (p > 32 ? 32 : p);
 }
 
 static int step_once(SkyjoHandle *h, const void *actions, int dtype, bool policy, cudaStream_t s) {

@@ -38,6 +38,7 @@ PY
 exit 0
 fi
 if [ "$4" = "multi" ]; then
+COMMON="${COMMON/--e2e-steps 40/--e2e-steps 100}"
 run auto
 run raw SKYJO_HOST_WIRE=raw
 run mix4 SKYJO_HOST_MIX=4
