@@ -523,13 +523,62 @@ def run_policy_rollout(args, dev):
 
     value, ms_per_step = timed(False)          # fp32, the reference's precision (RLlib TorchFC)
     value_bf16, ms_bf16 = timed(True)          # the same policy under bf16 autocast (library tensor-core GEMMs)
+    out = {"value": value, "unit": UNIT, "envs": B, "steps": T, "ms_per_step": ms_per_step,
+           "policy": "ActionMaskPolicy 2x256 tanh + value branch, fp32 (ATen GEMMs), fused masked-softmax-sample kernel",
+           "bf16_autocast": {"value": value_bf16, "ms_per_step": ms_bf16},
+           "zero_copy": True, "reset": "same_step"}
+    # the same loop with the policy side as ONE sm_100a kernel (csrc/skyjo_policy.cu: tcgen05.mma, weights in shared
+    # memory, activations in tensor memory, tanh / masked softmax / Philox sample in the epilogues)
+    if env.obs_len <= 96:
+        from skyjo_rl_b200.policy import FusedPolicy
+        fused = FusedPolicy(policy, env, with_value=False)
+        acts = torch.empty(B, dtype=torch.uint8, device=dev)
+        logp = torch.empty(B, dtype=torch.float32, device=dev)
+
+        def fsteps(n):
+            for t in range(n):
+                fused.sample(t, acts, logp)
+                env.step(acts)
+
+        fsteps(8)
+        Tf = max(T, 200)
+        env.clear_stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        fsteps(Tf)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        ms = ev0.elapsed_time(ev1)
+        st = env.stats()
+        assert st["illegal"] == 0
+        # the policy kernel alone, back to back on the same observations
+        ev0.record()
+        for t in range(50):
+            fused.sample(t, acts, logp)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        k_us = 1e3 * ev0.elapsed_time(ev1) / 50
+        flop_issued = 2.0 * B * ((96 + 256) * 256 + 256 * 32)       # the MMAs the kernel issues (K padded to 96, N to 32)
+        flop_useful = 2.0 * B * (env.obs_len * 256 + 256 * 256 + 256 * 26)
+        peak_tf = None
+        try:
+            peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:  # noqa: BLE001
+            peak_tf = 1590.0
+        out["fused_kernel"] = {
+            "value": st["steps"] / (ms * 1e-3), "unit": UNIT, "steps": Tf, "ms_per_step": ms / Tf,
+            "kernel": "skyjo::policy_kernel (tcgen05.mma kind::f16, A from tensor memory) + skyjo::step_kernel",
+            "policy_kernel_us": k_us, "tflops_issued": flop_issued / (k_us * 1e-6) / 1e12,
+            "tflops_useful": flop_useful / (k_us * 1e-6) / 1e12, "peak_bf16_tflops": peak_tf,
+            "tensor_frac_issued": flop_issued / (k_us * 1e-6) / 1e12 / peak_tf,
+            "sfu_bound_us": B * 512 / (148 * 16 * 1.965e9) * 1e6,
+            "note": "bf16 operands, fp32 accumulation; 512 tanh per env on the SFUs (16 per clock per SM) bound the "
+                    "kernel before the tensor cores do (sfu_bound_us at 1965 MHz)"}
     env.check()
     assert ptr == (env.observations.data_ptr(), env.action_mask.data_ptr()), "obs / mask must be consumed in place"
     env.close()
-    return {"value": value, "unit": UNIT, "envs": B, "steps": T, "ms_per_step": ms_per_step,
-            "policy": "ActionMaskPolicy 2x256 tanh + value branch, fp32 (ATen GEMMs), fused masked-softmax-sample kernel",
-            "bf16_autocast": {"value": value_bf16, "ms_per_step": ms_bf16},
-            "zero_copy": True, "reset": "same_step"}
+    return out
 
 
 def run_e2e(args, env, dev, rank, world):

@@ -280,6 +280,28 @@ int skyjo_stats_clear(SkyjoHandle *h, void *stream);
 int skyjo_sample_actions(SkyjoHandle *h, const float *logits_dev, const int8_t *mask_dev,
                          uint64_t sample_seed, uint8_t *actions_dev, float *logp_dev,
                          float *entropy_dev, void *stream);
+/* The whole policy side of a rollout step in ONE kernel (csrc/skyjo_policy.cu): the reference's action-mask model
+ * (action_mask_model.py:58-77: RLlib TorchFC, two tanh layers of 256, logits + clamp(log(mask), FLOAT_MIN)) evaluated
+ * on the bound int8 observation rows in place -- bf16 operands, fp32 accumulation, tcgen05.mma with the three weight
+ * matrices resident in shared memory and every activation in tensor memory -- then the masked softmax + categorical
+ * sample of skyjo_sample_actions (same Philox keying: equal logits draw equal actions).  Observation rows of at most
+ * 96 bytes (direct mode up to 6 players, or indirect mode); functional (bf16) parity with an fp32 evaluation, the
+ * tolerance is stated in tests/test_gpu_fused_policy.py.
+ *   skyjo_policy_pack: float32 torch.nn.Linear parameters (w[out][in] row-major, device pointers: w1 [256, obs_len],
+ *     b1 [256], w2 [256, 256], b2 [256], w3 [n_out, 256], b3 [n_out]; n_out = 26 for the logits net, 1 for a value
+ *     head) -> the kernel's weight image (skyjo_policy_packed_bytes() bytes of device memory, 16-byte aligned).
+ *   skyjo_policy_sample: actions uint8[B] (feed them to skyjo_step), and if not null logp float32[B] of the drawn
+ *     action, entropy float32[B] of the masked distribution, the unmasked logits float32[B, 26].
+ *   skyjo_policy_value: value float32[B] from a packed value head.
+ *   skyjo_policy_debug: logits and the pre-activations float32[B, 256] of the two hidden layers (parity tests). */
+int64_t skyjo_policy_packed_bytes(void);
+int skyjo_policy_pack(int obs_len, int n_out, const float *w1_dev, const float *b1_dev, const float *w2_dev,
+                      const float *b2_dev, const float *w3_dev, const float *b3_dev, void *packed_dev, void *stream);
+int skyjo_policy_sample(SkyjoHandle *h, const void *packed_dev, uint64_t sample_seed, uint8_t *actions_dev,
+                        float *logp_dev, float *entropy_dev, float *logits_dev, void *stream);
+int skyjo_policy_value(SkyjoHandle *h, const void *packed_dev, float *value_dev, void *stream);
+int skyjo_policy_debug(SkyjoHandle *h, const void *packed_dev, float *pre1_dev, float *pre2_dev, float *logits_dev,
+                       void *stream);
 /* Closes the running refill window and makes `stream` wait for the library's internal streams:
  * work queued on `stream` afterwards may read or overwrite the state buffer (checkpointing). */
 int skyjo_quiesce(SkyjoHandle *h, void *stream);

@@ -49,7 +49,8 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(OBJ, "skyjo_capi.o"), []),
-            (os.path.join(CSRC, "skyjo_hostsimd.cpp"), os.path.join(OBJ, "skyjo_hostsimd.o"), [])]
+            (os.path.join(CSRC, "skyjo_hostsimd.cpp"), os.path.join(OBJ, "skyjo_hostsimd.o"), []),
+            (os.path.join(CSRC, "skyjo_policy.cu"), os.path.join(OBJ, "skyjo_policy.o"), [])]
     for n in range(1, 13):
         jobs.append((os.path.join(CSRC, "skyjo_step_inst.cu"), os.path.join(OBJ, f"skyjo_step_n{n}.o"), [f"-DSKYJO_N={n}"]))
     return _run(jobs, LIB, verbose)
@@ -65,7 +66,8 @@ def build_variant(out, defines=(), players=(4,), verbose=False):
     dflags = [f"-D{d}" for d in defines]
     mask = sum(1 << (n - 1) for n in players)
     jobs = [(os.path.join(CSRC, "skyjo_capi.cu"), os.path.join(obj, "skyjo_capi.o"), dflags + [f"-DSKYJO_ONLY_PLAYERS_MASK={mask}"]),
-            (os.path.join(CSRC, "skyjo_hostsimd.cpp"), os.path.join(obj, "skyjo_hostsimd.o"), [])]
+            (os.path.join(CSRC, "skyjo_hostsimd.cpp"), os.path.join(obj, "skyjo_hostsimd.o"), []),
+            (os.path.join(CSRC, "skyjo_policy.cu"), os.path.join(obj, "skyjo_policy.o"), dflags)]
     for n in players:
         jobs.append((os.path.join(CSRC, "skyjo_step_inst.cu"), os.path.join(obj, f"skyjo_step_n{n}.o"), dflags + [f"-DSKYJO_N={n}"]))
     return _run(jobs, out, verbose)

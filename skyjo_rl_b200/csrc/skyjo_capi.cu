@@ -16,6 +16,7 @@
 #include "skyjo_deal.cuh"
 #include "skyjo_hostio.cuh"
 #include "skyjo_hostsimd.h"
+#include "skyjo_policy.h"
 #include "skyjo_rng.cuh"
 #include "skyjo_sample.cuh"
 #include "skyjo_state.cuh"
@@ -1164,6 +1165,73 @@ int skyjo_sample_actions(SkyjoHandle *h, const float *logits_dev, const int8_t *
     h->launches += 1;
     CU(cudaGetLastError());
     return SKYJO_OK;
+}
+
+// ---- fused policy forward (csrc/skyjo_policy.cu) ----------------------------------------------------------------
+int64_t skyjo_policy_packed_bytes(void) { return POLICY_PACKED_BYTES; }
+
+int skyjo_policy_pack(int obs_len, int n_out, const float *w1, const float *b1, const float *w2, const float *b2,
+                      const float *w3, const float *b3, void *packed_dev, void *stream) {
+    if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !packed_dev) return fail(SKYJO_E_INVALID, "null argument");
+    if (obs_len < 1 || obs_len > POLICY_MAX_OBS)
+        return fail(SKYJO_E_INVALID, "the fused policy kernel takes observation rows of at most 96 bytes (direct mode up to 6 players, or indirect)");
+    if (n_out < 1 || n_out > 26) return fail(SKYJO_E_INVALID, "n_out must be 26 (logits) or 1 (value head)");
+    if (((uintptr_t)packed_dev & 15) != 0) return fail(SKYJO_E_INVALID, "packed buffer must be 16-byte aligned");
+    CU(launch_policy_pack(w1, b1, w2, b2, w3, b3, obs_len, n_out, packed_dev, (cudaStream_t)stream));
+    return SKYJO_OK;
+}
+
+static int policy_launch(SkyjoHandle *h, const void *packed_dev, PolicyParams &p, void *stream) {
+    if (!h || !packed_dev) return fail(SKYJO_E_INVALID, "null argument");
+    if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
+    if (h->obs_len > POLICY_MAX_OBS) return fail(SKYJO_E_INVALID, "observation rows longer than 96 bytes: use a library policy");
+    if (((uintptr_t)packed_dev & 15) != 0) return fail(SKYJO_E_INVALID, "packed buffer must be 16-byte aligned");
+    CU(cudaSetDevice(h->device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    p.obs = (const int8_t *)h->outs.obs_dev;
+    p.mask = (const int8_t *)h->outs.action_mask_dev;
+    p.packed = (const uint8_t *)packed_dev;
+    p.B = h->B;
+    p.D = h->obs_len;
+    p.bulk_ok = h->bulk_ok;
+    p.first_env = h->first_env;
+    p.t = h->t;
+    CU(launch_policy(p, sms, (cudaStream_t)stream));
+    h->launches += 1;
+    return SKYJO_OK;
+}
+
+int skyjo_policy_sample(SkyjoHandle *h, const void *packed_dev, uint64_t sample_seed, uint8_t *actions_dev,
+                        float *logp_dev, float *entropy_dev, float *logits_dev, void *stream) {
+    if (!actions_dev) return fail(SKYJO_E_INVALID, "null argument");
+    PolicyParams p;
+    memset(&p, 0, sizeof(p));
+    p.seed = sample_seed;
+    p.actions = actions_dev;
+    p.logp = logp_dev;
+    p.entropy = entropy_dev;
+    p.logits = logits_dev;
+    return policy_launch(h, packed_dev, p, stream);
+}
+
+int skyjo_policy_value(SkyjoHandle *h, const void *packed_dev, float *value_dev, void *stream) {
+    if (!value_dev) return fail(SKYJO_E_INVALID, "null argument");
+    PolicyParams p;
+    memset(&p, 0, sizeof(p));
+    p.value = value_dev;
+    return policy_launch(h, packed_dev, p, stream);
+}
+
+int skyjo_policy_debug(SkyjoHandle *h, const void *packed_dev, float *pre1_dev, float *pre2_dev, float *logits_dev,
+                       void *stream) {
+    if (!logits_dev) return fail(SKYJO_E_INVALID, "null argument");
+    PolicyParams p;
+    memset(&p, 0, sizeof(p));
+    p.logits = logits_dev;
+    p.dbg1 = pre1_dev;
+    p.dbg2 = pre2_dev;
+    return policy_launch(h, packed_dev, p, stream);
 }
 
 int skyjo_quiesce(SkyjoHandle *h, void *stream) {

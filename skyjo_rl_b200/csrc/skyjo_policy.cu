@@ -1,0 +1,400 @@
+// skyjo_policy.cu -- the consumer side of BASELINE config 4 as ONE sm_100a kernel: the action-mask policy of the
+// reference (rlskyjo/models/action_mask_model.py:58-77 -- RLlib's TorchFC with fcnet_hiddens [256, 256], tanh,
+// logits + clamp(log(mask), FLOAT_MIN)) evaluated on the env's int8 observation rows in place, followed by the
+// masked softmax + categorical sample that emits the uint8 actions skyjo_step consumes.
+//
+//   obs int8[B, D] --bf16--> [x W1^T + b1] -tanh-> [h1 W2^T + b2] -tanh-> [h2 W3^T + b3] -> mask, softmax, sample
+//
+// The three matrix products are the only contractions near the hot path, and they run on the 5th-generation
+// tensor cores: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in tensor memory), M = 128 envs per
+// tile, issued by one thread.  Layout of one persistent CTA (one per SM, 160 threads):
+//   * shared memory holds the three weight matrices for the whole launch (bf16, 192 KB, in the canonical K-major
+//     no-swizzle core-matrix layout the MMA descriptors address: 8 rows x 16 bytes per core matrix), the biases,
+//     and the obs / mask rows of the tile being started (1-D TMA bulk copies, one tile ahead);
+//   * tensor memory (all 512 columns x 128 lanes) holds every activation: an env is a TMEM lane.  The A operand
+//     of each product is read FROM TENSOR MEMORY (tcgen05.mma with a TMEM A address), so activations never touch
+//     shared memory: warps 0-3 (one thread per env) convert the obs row to bf16 and tcgen05.st it, and after each
+//     hidden layer read the fp32 accumulators with tcgen05.ld, add the bias, apply tanh, pack to bf16 and store
+//     them back in place (the 256 fp32 columns of a layer compact into 128 columns of bf16 pairs);
+//   * warp 4, lane 0 issues the MMAs: 6 + 16 + 16 per tile, tcgen05.commit onto an mbarrier after each layer.
+// Column map: R1 = [0, 256): D1 (layer-1 accumulators) -> h1 as bf16 in [0, 128); D3 (logits) in [128, 160).
+//             R2 = [256, 512): obs as bf16 in [256, 304) -> D2 -> h2 as bf16 in [256, 384).
+// Roofline (tensor): 2 x (96 + 256) x 256 + 2 x 256 x 32 = 196 608 FLOP per env as issued (178 688 useful), and
+// 512 tanh per env on the SFUs (16 per clock per SM), which is the longer of the two per tile; see DESIGN.md.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "skyjo_policy.h"
+#define SKYJO_SAMPLE_DEVICE_ONLY
+#include "skyjo_sample.cuh"
+
+namespace skyjo {
+
+constexpr int POL_THREADS = 160;  // warps 0-3: one thread per env (TMEM lane); warp 4: MMA issue
+constexpr int POL_N3 = 32;        // 26 logits (or 1 value) padded to an MMA N
+constexpr uint32_t OFF_W1 = 0;
+constexpr uint32_t OFF_W2 = OFF_W1 + POLICY_K1 * POLICY_HIDDEN * 2;
+constexpr uint32_t OFF_W3 = OFF_W2 + POLICY_HIDDEN * POLICY_HIDDEN * 2;
+constexpr uint32_t OFF_B1 = OFF_W3 + POLICY_HIDDEN * POL_N3 * 2;
+constexpr uint32_t OFF_B2 = OFF_B1 + POLICY_HIDDEN * 4;
+constexpr uint32_t OFF_B3 = OFF_B2 + POLICY_HIDDEN * 4;
+constexpr uint32_t PACKED_BYTES = OFF_B3 + POL_N3 * 4;
+static_assert(PACKED_BYTES == POLICY_PACKED_BYTES, "skyjo_policy.h out of date");
+constexpr uint32_t OFF_OBS = PACKED_BYTES;                                   // 128 rows of up to POLICY_MAX_OBS bytes
+constexpr uint32_t OFF_MASK = OFF_OBS + ((POLICY_TILE * POLICY_MAX_OBS + 127) / 128) * 128;
+constexpr uint32_t OFF_BAR = OFF_MASK + POLICY_TILE * 26;                    // 3328 = 26 * 128
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
+static_assert(SMEM_BYTES <= 227 * 1024, "policy kernel shared memory");
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]; bf16 x bf16 -> fp32
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 bits x 32 columns: thread i of the warp reads lane (warp % 4) * 32 + i, columns [col, col + 32)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {  // element 2j in the low half
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&p);
+}
+
+// K-major operand in the canonical no-swizzle layout: element (r, k) of an R x K matrix at
+//   ((k / 8) * (R / 8) + r / 8) * 128 + (r % 8) * 16 + (k % 8) * 2        bytes,
+// i.e. 8 x 8 core matrices of 128 contiguous bytes; consecutive 8-row groups 128 B apart (the descriptor's
+// stride-dimension byte offset), the two K-halves of one K = 16 MMA (R / 8) * 128 B apart (leading-dimension
+// byte offset).  cute::UMMA::SmemDescriptor: start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46),
+// version 1 in [46,48), layout type 0 (no swizzle) in [61,64).
+__host__ __device__ inline uint32_t kmajor_offset(uint32_t r, uint32_t k, uint32_t R) {
+    return ((k >> 3) * (R >> 3) + (r >> 3)) * 128u + (r & 7u) * 16u + (k & 7u) * 2u;
+}
+__device__ __forceinline__ uint64_t b_desc(uint32_t smem_addr, uint32_t R) {
+    const uint64_t lbo = (uint64_t)((R >> 3) * 128u) >> 4, sbo = 128u >> 4;
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) at [4,6), a/b format BF16 (1) at [7,10) / [10,13), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// tanh(acc + bias) of the 256 fp32 columns at `src`, packed to 128 columns of bf16 pairs at `dst` (same lanes;
+// dst <= src, so a chunk is written only after it has been read)
+__device__ __forceinline__ void hidden_epilogue(uint32_t src, uint32_t dst, const float *s_bias, float *dbg_row) {
+#pragma unroll 1
+    for (int c = 0; c < POLICY_HIDDEN / 32; ++c) {
+        uint32_t v[32];
+        tc_ld32(src + 32 * c, v);
+        tc_wait_ld();
+        if (dbg_row) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dbg_row[32 * c + i] = __uint_as_float(v[i]) + s_bias[32 * c + i];
+        }
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float2 b = *reinterpret_cast<const float2 *>(s_bias + 32 * c + 2 * j);
+            w[j] = pack_bf16x2(tanh_fast(__uint_as_float(v[2 * j]) + b.x), tanh_fast(__uint_as_float(v[2 * j + 1]) + b.y));
+        }
+        tc_st16(dst + 16 * c, w);
+    }
+    tc_wait_st();
+}
+
+__global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_constant__ PolicyParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sm = smem_u32(smem);
+    const uint32_t bar_w = sm + OFF_BAR, bar_in = bar_w + 8, bar_a = bar_w + 16, bar_d = bar_w + 24;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 32);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long n_tiles = (p.B + POLICY_TILE - 1) / POLICY_TILE;
+    const int D = p.D;
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_in, 1);
+        mbar_init(bar_a, POLICY_TILE);
+        mbar_init(bar_d, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {  // one warp allocates all of tensor memory (one CTA per SM: 200 KB of shared memory)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // a tile whose 128 rows exist travels by bulk copy; the ragged last tile of the batch by plain loads
+    auto tile_is_bulk = [&](long long tile) { return p.bulk_ok && (tile + 1) * POLICY_TILE <= p.B; };
+    auto issue_tile = [&](long long tile) {
+        const uint32_t ob = (uint32_t)(POLICY_TILE * D), mb = POLICY_TILE * 26u;
+        mbar_expect_tx(bar_in, ob + mb);
+        bulk_load(sm + OFF_OBS, p.obs + tile * POLICY_TILE * D, ob, bar_in);
+        bulk_load(sm + OFF_MASK, p.mask + tile * POLICY_TILE * 26, mb, bar_in);
+    };
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, PACKED_BYTES);
+        for (uint32_t off = 0; off < PACKED_BYTES; off += 32768u) {
+            const uint32_t n = PACKED_BYTES - off < 32768u ? PACKED_BYTES - off : 32768u;
+            bulk_load(sm + off, p.packed + off, n, bar_w);
+        }
+        if ((long long)blockIdx.x < n_tiles && tile_is_bulk(blockIdx.x)) issue_tile(blockIdx.x);
+    }
+
+    if (warp < 4) {
+        // ---- one thread per env: operand staging, the two hidden epilogues, the output epilogue ----------------
+        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+        const uint32_t R1 = tmem + lane_base, R2 = tmem + lane_base + 256u;
+        const float *s_b1 = reinterpret_cast<const float *>(smem + OFF_B1);
+        const float *s_b2 = reinterpret_cast<const float *>(smem + OFF_B2);
+        const float *s_b3 = reinterpret_cast<const float *>(smem + OFF_B3);
+        const int8_t *s_obs = reinterpret_cast<const int8_t *>(smem + OFF_OBS);
+        const int8_t *s_mask = reinterpret_cast<const int8_t *>(smem + OFF_MASK);
+        uint32_t ph_in = 0, ph_d = 0;
+        mbar_wait(bar_w, 0);
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long e = tile * POLICY_TILE + tid;
+            const bool valid = e < p.B;
+            if (tile_is_bulk(tile)) {
+                mbar_wait(bar_in, ph_in);
+                ph_in ^= 1u;
+            } else {
+                const long long rows = p.B - tile * POLICY_TILE < POLICY_TILE ? p.B - tile * POLICY_TILE : POLICY_TILE;
+                for (int i = tid; i < rows * D; i += POLICY_TILE) smem[OFF_OBS + i] = (uint8_t)p.obs[tile * POLICY_TILE * D + i];
+                for (int i = tid; i < rows * 26; i += POLICY_TILE) smem[OFF_MASK + i] = (uint8_t)p.mask[tile * POLICY_TILE * 26 + i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            // the env's observation row as bf16 pairs (exact: -24 .. 127), zero beyond D; its legal-action bits
+            uint32_t legal = 0;
+            {
+                const int8_t *row = s_obs + tid * D;
+#pragma unroll
+                for (int g = 0; g < POLICY_K1 / 32; ++g) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = 32 * g + 2 * j;
+                        const float x0 = (valid && k < D) ? (float)row[k] : 0.f;
+                        const float x1 = (valid && k + 1 < D) ? (float)row[k + 1] : 0.f;
+                        w[j] = pack_bf16x2(x0, x1);
+                    }
+                    tc_st16(R2 + 16 * g, w);
+                }
+                if (valid) {
+                    const int8_t *mr = s_mask + tid * 26;
+#pragma unroll
+                    for (int a = 0; a < 26; ++a) legal |= (mr[a] != 0 ? 1u : 0u) << a;
+                }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_a);
+            // every row of the tile has been read: the next tile's rows may land
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0 && tile + gridDim.x < n_tiles && tile_is_bulk(tile + gridDim.x)) issue_tile(tile + gridDim.x);
+
+            mbar_wait(bar_d, ph_d);  // D1 = x W1^T
+            ph_d ^= 1u;
+            tc_fence_after();
+            hidden_epilogue(R1, R1, s_b1, (p.dbg1 && valid) ? p.dbg1 + e * POLICY_HIDDEN : nullptr);
+            tc_fence_before();
+            mbar_arrive(bar_a);
+
+            mbar_wait(bar_d, ph_d);  // D2 = h1 W2^T
+            ph_d ^= 1u;
+            tc_fence_after();
+            hidden_epilogue(R2, R2, s_b2, (p.dbg2 && valid) ? p.dbg2 + e * POLICY_HIDDEN : nullptr);
+            tc_fence_before();
+            mbar_arrive(bar_a);
+
+            mbar_wait(bar_d, ph_d);  // D3 = h2 W3^T
+            ph_d ^= 1u;
+            tc_fence_after();
+            uint32_t v[32];
+            tc_ld32(R1 + 128u, v);
+            tc_wait_ld();
+            if (valid) {
+                if (p.value) {
+                    p.value[e] = __uint_as_float(v[0]) + s_b3[0];
+                } else {
+                    float l[26];
+#pragma unroll
+                    for (int a = 0; a < 26; ++a) l[a] = __uint_as_float(v[a]) + s_b3[a];
+                    if (p.logits) {
+#pragma unroll
+                        for (int a = 0; a < 26; ++a) p.logits[e * 26 + a] = l[a];
+                    }
+                    if (p.actions) {
+                        if (legal == 0) {  // cannot happen for a live env; keep the step well defined
+                            p.actions[e] = 255;
+                            if (p.logp) p.logp[e] = 0.f;
+                            if (p.entropy) p.entropy[e] = 0.f;
+                        } else {
+                            int act;
+                            float lp, ent;
+                            sample_masked(l, legal, p.seed, p.first_env + (unsigned long long)e, p.t, act, lp, ent);
+                            p.actions[e] = (uint8_t)act;
+                            if (p.logp) p.logp[e] = lp;
+                            if (p.entropy) p.entropy[e] = ent;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();  // the D3 / h2 columns are rewritten by the next tile's operand store and MMA
+        }
+    } else {
+        // ---- the MMA warp: 6 + 16 + 16 tcgen05.mma per tile, issued by lane 0; A from tensor memory, B from shared memory
+        constexpr uint32_t I256 = idesc_bf16(POLICY_TILE, POLICY_HIDDEN), I32 = idesc_bf16(POLICY_TILE, POL_N3);
+        constexpr uint32_t KSTEP_H = 2u * (POLICY_HIDDEN / 8) * 128u;  // bytes between K = 16 slices of W1 / W2
+        constexpr uint32_t KSTEP_3 = 2u * (POL_N3 / 8) * 128u;
+        uint32_t ph_a = 0;
+        mbar_wait(bar_w, 0);
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(bar_a, ph_a);
+            ph_a ^= 1u;
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (uint32_t k = 0; k < POLICY_K1 / 16; ++k)
+                    tc_mma_ts(tmem, tmem + 256u + 8u * k, b_desc(sm + OFF_W1 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
+                tc_commit(bar_d);
+            }
+            __syncwarp();
+            mbar_wait(bar_a, ph_a);
+            ph_a ^= 1u;
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (uint32_t k = 0; k < POLICY_HIDDEN / 16; ++k)
+                    tc_mma_ts(tmem + 256u, tmem + 8u * k, b_desc(sm + OFF_W2 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
+                tc_commit(bar_d);
+            }
+            __syncwarp();
+            mbar_wait(bar_a, ph_a);
+            ph_a ^= 1u;
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (uint32_t k = 0; k < POLICY_HIDDEN / 16; ++k)
+                    tc_mma_ts(tmem + 128u, tmem + 256u + 8u * k, b_desc(sm + OFF_W3 + k * KSTEP_3, POL_N3), I32, k);
+                tc_commit(bar_d);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// fp32 torch.nn.Linear weights (W[out][in], row-major) -> the kernel's shared-memory image
+__global__ void policy_pack_kernel(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                                   const float *b3, int D, int n_out, uint8_t *packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __nv_bfloat16 *W1 = reinterpret_cast<__nv_bfloat16 *>(packed + OFF_W1);
+    __nv_bfloat16 *W2 = reinterpret_cast<__nv_bfloat16 *>(packed + OFF_W2);
+    __nv_bfloat16 *W3 = reinterpret_cast<__nv_bfloat16 *>(packed + OFF_W3);
+    if (i < POLICY_K1 * POLICY_HIDDEN) {
+        const int n = i / POLICY_K1, k = i % POLICY_K1;
+        W1[kmajor_offset(n, k, POLICY_HIDDEN) / 2] = __float2bfloat16_rn(k < D ? w1[n * D + k] : 0.f);
+    }
+    if (i < POLICY_HIDDEN * POLICY_HIDDEN) {
+        const int n = i / POLICY_HIDDEN, k = i % POLICY_HIDDEN;
+        W2[kmajor_offset(n, k, POLICY_HIDDEN) / 2] = __float2bfloat16_rn(w2[n * POLICY_HIDDEN + k]);
+    }
+    if (i < POL_N3 * POLICY_HIDDEN) {
+        const int n = i / POLICY_HIDDEN, k = i % POLICY_HIDDEN;
+        W3[kmajor_offset(n, k, POL_N3) / 2] = __float2bfloat16_rn(n < n_out ? w3[n * POLICY_HIDDEN + k] : 0.f);
+    }
+    if (i < POLICY_HIDDEN) {
+        reinterpret_cast<float *>(packed + OFF_B1)[i] = b1[i];
+        reinterpret_cast<float *>(packed + OFF_B2)[i] = b2[i];
+    }
+    if (i < POL_N3) reinterpret_cast<float *>(packed + OFF_B3)[i] = i < n_out ? b3[i] : 0.f;
+}
+
+cudaError_t launch_policy_pack(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                               const float *b3, int D, int n_out, void *packed, cudaStream_t s) {
+    const int n = POLICY_HIDDEN * POLICY_HIDDEN;
+    policy_pack_kernel<<<(n + 255) / 256, 256, 0, s>>>(w1, b1, w2, b2, w3, b3, D, n_out, (uint8_t *)packed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_policy(const PolicyParams &p, int sm_count, cudaStream_t s) {
+    const cudaError_t e = cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    const long long n_tiles = (p.B + POLICY_TILE - 1) / POLICY_TILE;
+    const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
+    policy_kernel<<<grid, POL_THREADS, SMEM_BYTES, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace skyjo

@@ -16,6 +16,49 @@ namespace skyjo {
 
 enum : uint32_t { PURPOSE_SAMPLE = 5 };
 
+// Masked softmax + inverse-CDF sample of one action from 26 logits (l is overwritten with the unnormalised
+// weights).  `legal` != 0: bit a = action a is legal.  Shared by sample_actions_kernel and the fused policy
+// kernel (skyjo_policy.cu), so that equal logits draw equal actions.
+__device__ __forceinline__ void sample_masked(float (&l)[26], uint32_t legal, unsigned long long seed,
+                                              unsigned long long genv, unsigned long long t, int &act, float &logp,
+                                              float &entropy) {
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int a = 0; a < 26; ++a)
+        if ((legal >> a) & 1u) mx = fmaxf(mx, l[a]);
+    float sum = 0.f, wsum = 0.f;  // sum of exp(l - mx), sum of exp(l - mx) * (l - mx) over legal actions
+#pragma unroll
+    for (int a = 0; a < 26; ++a) {
+        const float d = l[a] - mx;
+        const float w = ((legal >> a) & 1u) ? expf(d) : 0.f;
+        l[a] = w;
+        sum += w;
+        wsum += w * (((legal >> a) & 1u) ? d : 0.f);
+    }
+    const U4 r = rng_block(seed, genv, PURPOSE_SAMPLE, (uint32_t)t, (uint32_t)(t >> 32));
+    const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);  // [0, 1) with 24 bits
+    const float target = u * sum;
+    act = 31 - __clz((int)legal);  // last legal action: the fallback when rounding leaves cum <= target
+    float cum = 0.f;
+    bool found = false;
+#pragma unroll
+    for (int a = 0; a < 26; ++a) {
+        cum += l[a];
+        if (!found && ((legal >> a) & 1u) && cum > target) {
+            act = a;
+            found = true;
+        }
+    }
+    float wa = 0.f;
+#pragma unroll
+    for (int a = 0; a < 26; ++a)
+        if (a == act) wa = l[a];
+    const float logz = logf(sum);
+    logp = logf(wa) - logz;
+    entropy = logz - wsum / sum;  // -sum p log p
+}
+
+#ifndef SKYJO_SAMPLE_DEVICE_ONLY  // skyjo_policy.cu only wants sample_masked
 __global__ void __launch_bounds__(128) sample_actions_kernel(const float *__restrict__ logits,
                                                              const int8_t *__restrict__ mask, long long B,
                                                              unsigned long long first_env, unsigned long long seed,
@@ -45,41 +88,13 @@ __global__ void __launch_bounds__(128) sample_actions_kernel(const float *__rest
         if (entropy) entropy[e] = 0.f;
         return;
     }
-    float mx = -3.0e38f;
-#pragma unroll
-    for (int a = 0; a < 26; ++a)
-        if ((legal >> a) & 1u) mx = fmaxf(mx, l[a]);
-    float sum = 0.f, wsum = 0.f;  // sum of exp(l - mx), sum of exp(l - mx) * (l - mx) over legal actions
-#pragma unroll
-    for (int a = 0; a < 26; ++a) {
-        const float d = l[a] - mx;
-        const float w = ((legal >> a) & 1u) ? expf(d) : 0.f;
-        l[a] = w;
-        sum += w;
-        wsum += w * (((legal >> a) & 1u) ? d : 0.f);
-    }
-    const U4 r = rng_block(seed, first_env + (unsigned long long)e, PURPOSE_SAMPLE, (uint32_t)t, (uint32_t)(t >> 32));
-    const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);  // [0, 1) with 24 bits
-    const float target = u * sum;
-    int act = 31 - __clz((int)legal);  // last legal action: the fallback when rounding leaves cum <= target
-    float cum = 0.f;
-    bool found = false;
-#pragma unroll
-    for (int a = 0; a < 26; ++a) {
-        cum += l[a];
-        if (!found && ((legal >> a) & 1u) && cum > target) {
-            act = a;
-            found = true;
-        }
-    }
-    float wa = 0.f;
-#pragma unroll
-    for (int a = 0; a < 26; ++a)
-        if (a == act) wa = l[a];
-    const float logz = logf(sum);
+    int act;
+    float lp, ent;
+    sample_masked(l, legal, seed, first_env + (unsigned long long)e, t, act, lp, ent);
     actions[e] = (uint8_t)act;
-    logp[e] = logf(wa) - logz;
-    if (entropy) entropy[e] = logz - wsum / sum;  // -sum p log p
+    logp[e] = lp;
+    if (entropy) entropy[e] = ent;
 }
+#endif
 
 }  // namespace skyjo
