@@ -13,14 +13,18 @@
 //     and the obs / mask rows of the tile being started (1-D TMA bulk copies, one tile ahead);
 //   * tensor memory (all 512 columns x 128 lanes) holds every activation: an env is a TMEM lane.  The A operand
 //     of each product is read FROM TENSOR MEMORY (tcgen05.mma with a TMEM A address), so activations never touch
-//     shared memory: warps 0-3 (one thread per env) convert the obs row to bf16 and tcgen05.st it, and after each
-//     hidden layer read the fp32 accumulators with tcgen05.ld, add the bias, apply tanh, pack to bf16 and store
-//     them back in place (the 256 fp32 columns of a layer compact into 128 columns of bf16 pairs);
-//   * warp 4, lane 0 issues the MMAs: 6 + 16 + 16 per tile, tcgen05.commit onto an mbarrier after each layer.
-// Column map: R1 = [0, 256): D1 (layer-1 accumulators) -> h1 as bf16 in [0, 128); D3 (logits) in [128, 160).
-//             R2 = [256, 512): obs as bf16 in [256, 304) -> D2 -> h2 as bf16 in [256, 384).
-// Roofline (tensor): 2 x (96 + 256) x 256 + 2 x 256 x 32 = 196 608 FLOP per env as issued (178 688 useful), and
-// 512 tanh per env on the SFUs (16 per clock per SM), which is the longer of the two per tile; see DESIGN.md.
+//     shared memory: warps 0-3 (one thread per env) convert the obs row to bf16 and tcgen05.st it; after each hidden
+//     layer warps 0-7 (two per scheduler, so that one's TMEM round trips hide behind the other's tanh; warps w and
+//     w + 4 own the same 32 lanes and one half of the 256 hidden units each) read the fp32 accumulators with
+//     tcgen05.ld, add the bias, apply tanh, pack to bf16 and store them back in place (a 32-column chunk of fp32
+//     compacts into 16 columns of bf16 pairs at the start of its half), announcing every chunk on an mbarrier;
+//   * warp 8, lane 0 issues the MMAs: 6 + 16 + 16 per tile -- those of layers 2 and 3 two at a time (K = 32) behind
+//     the epilogue chunk that produces their operand -- and tcgen05.commit's each layer onto an mbarrier.
+// Column map: R1 = [0, 256): D1 -> h1 as bf16 in [0, 64) and [128, 192); D3 (logits) in [64, 96).
+//             R2 = [256, 512): obs as bf16 in [256, 304) -> D2 -> h2 as bf16 in [256, 320) and [384, 448).
+// Roofline: 2 x (96 + 256) x 256 + 2 x 256 x 32 = 196 608 FLOP per env as issued (178 688 useful) on the tensor cores,
+// and 512 tanh per env on the SFUs (MUFU.TANH: 16 XU-pipe cycles per warp instruction), which is the longer of the
+// two per tile: 57 us per 2^18 envs at 1.965 GHz against 22 us of MMA time; see DESIGN.md.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,7 +35,10 @@
 
 namespace skyjo {
 
-constexpr int POL_THREADS = 160;  // warps 0-3: one thread per env (TMEM lane); warp 4: MMA issue
+constexpr int POL_THREADS = 288;  // warps 0-7: two threads per env (TMEM lane = tid & 127), half of the hidden units each;
+                                  // warp 8: MMA issue
+constexpr int POL_MMA_WARP = 8;
+constexpr uint32_t POL_D3_COL = 64;  // logits accumulate in columns [64, 96) of R1
 constexpr int POL_N3 = 32;        // 26 logits (or 1 value) padded to an MMA N
 constexpr uint32_t OFF_W1 = 0;
 constexpr uint32_t OFF_W2 = OFF_W1 + POLICY_K1 * POLICY_HIDDEN * 2;
@@ -44,7 +51,7 @@ static_assert(PACKED_BYTES == POLICY_PACKED_BYTES, "skyjo_policy.h out of date")
 constexpr uint32_t OFF_OBS = PACKED_BYTES;                                   // 128 rows of up to POLICY_MAX_OBS bytes
 constexpr uint32_t OFF_MASK = OFF_OBS + ((POLICY_TILE * POLICY_MAX_OBS + 127) / 128) * 128;
 constexpr uint32_t OFF_BAR = OFF_MASK + POLICY_TILE * 26;                    // 3328 = 26 * 128
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;  // 4 + 8 mbarriers, the TMEM base address
 static_assert(SMEM_BYTES <= 227 * 1024, "policy kernel shared memory");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -114,11 +121,6 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {  // element 2j in the low half
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t *>(&p);
@@ -143,13 +145,32 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-// tanh(acc + bias) of the 256 fp32 columns at `src`, packed to 128 columns of bf16 pairs at `dst` (same lanes;
-// dst <= src, so a chunk is written only after it has been read)
-__device__ __forceinline__ void hidden_epilogue(uint32_t src, uint32_t dst, const float *s_bias, float *dbg_row) {
+// tanh on the SFUs.  Measured on B200 (ncu, profiles/r2_policy_*): MUFU.TANH occupies the XU pipe for 16 cycles per
+// warp instruction (half the rate of ex2 / rcp), the packed bf16x2 form is issued as two MUFU.TANH.BF16, and
+// 1 - 2 / (exp2(2 log2(e) a) + 1) through ex2 + rcp costs the same 16 pipe cycles plus three more issue slots
+// (152 us against 112 us per 2^18 envs): 512 tanh per env bound this kernel at 2^18 x 512 x 16 / (32 x 4 x 148)
+// cycles = 57 us at 1.965 GHz, about three times its tensor-core time.
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
+    uint32_t y;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+
+// column (relative to its 256-column region) of the bf16 pairs of hidden units [32 c, 32 c + 32): chunks 0-3 compact
+// to the start of the first half, chunks 4-7 to the start of the second half, each over columns its own half of
+// the epilogue team has already read
+__host__ __device__ constexpr uint32_t hidden_col(uint32_t c) { return c < 4 ? 16u * c : 128u + 16u * (c - 4u); }
+
+// tanh(acc + bias) of one half (group 0: hidden units 0..127, group 1: 128..255) of the 256 fp32 columns of
+// `region`, packed to bf16 pairs in place (same lanes).  The sums are rounded to bf16 before the tanh
+// (tanh.approx.bf16x2: the result is the packed operand itself); the next layer's MMAs over K-chunk c start as soon
+// as all 128 rows have announced it on bar_h[c].
+__device__ __forceinline__ void hidden_epilogue(uint32_t region, int group, const float *s_bias, float *dbg_row,
+                                                uint32_t bar_h) {
 #pragma unroll 1
-    for (int c = 0; c < POLICY_HIDDEN / 32; ++c) {
+    for (int c = 4 * group; c < 4 * group + 4; ++c) {
         uint32_t v[32];
-        tc_ld32(src + 32 * c, v);
+        tc_ld32(region + 32 * c, v);
         tc_wait_ld();
         if (dbg_row) {
 #pragma unroll
@@ -159,18 +180,23 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t src, uint32_t dst, cons
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float2 b = *reinterpret_cast<const float2 *>(s_bias + 32 * c + 2 * j);
-            w[j] = pack_bf16x2(tanh_fast(__uint_as_float(v[2 * j]) + b.x), tanh_fast(__uint_as_float(v[2 * j + 1]) + b.y));
+            w[j] = tanh_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]) + b.x, __uint_as_float(v[2 * j + 1]) + b.y));
         }
-        tc_st16(dst + 16 * c, w);
+        tc_st16(region + hidden_col(c), w);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_h + 8 * c);
     }
-    tc_wait_st();
 }
 
 __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_constant__ PolicyParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sm = smem_u32(smem);
-    const uint32_t bar_w = sm + OFF_BAR, bar_in = bar_w + 8, bar_a = bar_w + 16, bar_d = bar_w + 24;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 32);
+    // bar_w: weights landed; bar_in: the tile's obs / mask rows landed; bar_a: the 128 obs rows are in tensor memory;
+    // bar_h[c]: chunk c (32 of the 256 hidden units) of the current hidden layer is in tensor memory as bf16;
+    // bar_d: the MMAs of a layer have completed (tcgen05.commit)
+    const uint32_t bar_w = sm + OFF_BAR, bar_in = bar_w + 8, bar_a = bar_w + 16, bar_d = bar_w + 24, bar_h = bar_w + 32;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 96);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_tiles = (p.B + POLICY_TILE - 1) / POLICY_TILE;
     const int D = p.D;
@@ -178,11 +204,12 @@ __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_con
     if (tid == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_in, 1);
-        mbar_init(bar_a, POLICY_TILE);
+        mbar_init(bar_a, 2 * POLICY_TILE);  // both halves of the epilogue team have left the previous tile
         mbar_init(bar_d, 1);
+        for (int c = 0; c < 8; ++c) mbar_init(bar_h + 8 * c, POLICY_TILE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {  // one warp allocates all of tensor memory (one CTA per SM: 200 KB of shared memory)
+    if (warp == POL_MMA_WARP) {  // one warp allocates all of tensor memory (one CTA per SM: 200 KB of shared memory)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -209,9 +236,10 @@ __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_con
         if ((long long)blockIdx.x < n_tiles && tile_is_bulk(blockIdx.x)) issue_tile(blockIdx.x);
     }
 
-    if (warp < 4) {
-        // ---- one thread per env: operand staging, the two hidden epilogues, the output epilogue ----------------
-        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+    if (warp < POL_MMA_WARP) {
+        // ---- the epilogue team: row = TMEM lane = tid & 127; group 0 (warps 0-3) also stages the operand and samples ---
+        const int group = warp >> 2, row = tid & (POLICY_TILE - 1);
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
         const uint32_t R1 = tmem + lane_base, R2 = tmem + lane_base + 256u;
         const float *s_b1 = reinterpret_cast<const float *>(smem + OFF_B1);
         const float *s_b2 = reinterpret_cast<const float *>(smem + OFF_B2);
@@ -221,101 +249,101 @@ __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_con
         uint32_t ph_in = 0, ph_d = 0;
         mbar_wait(bar_w, 0);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const long long e = tile * POLICY_TILE + tid;
+            const long long e = tile * POLICY_TILE + row;
             const bool valid = e < p.B;
-            if (tile_is_bulk(tile)) {
-                mbar_wait(bar_in, ph_in);
-                ph_in ^= 1u;
-            } else {
-                const long long rows = p.B - tile * POLICY_TILE < POLICY_TILE ? p.B - tile * POLICY_TILE : POLICY_TILE;
-                for (int i = tid; i < rows * D; i += POLICY_TILE) smem[OFF_OBS + i] = (uint8_t)p.obs[tile * POLICY_TILE * D + i];
-                for (int i = tid; i < rows * 26; i += POLICY_TILE) smem[OFF_MASK + i] = (uint8_t)p.mask[tile * POLICY_TILE * 26 + i];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            // the env's observation row as bf16 pairs (exact: -24 .. 127), zero beyond D; its legal-action bits
             uint32_t legal = 0;
-            {
-                const int8_t *row = s_obs + tid * D;
+            if (group == 0) {
+                if (tile_is_bulk(tile)) {
+                    mbar_wait(bar_in, ph_in);
+                    ph_in ^= 1u;
+                } else {
+                    const long long rows = p.B - tile * POLICY_TILE < POLICY_TILE ? p.B - tile * POLICY_TILE : POLICY_TILE;
+                    for (int i = row; i < rows * D; i += POLICY_TILE) smem[OFF_OBS + i] = (uint8_t)p.obs[tile * POLICY_TILE * D + i];
+                    for (int i = row; i < rows * 26; i += POLICY_TILE) smem[OFF_MASK + i] = (uint8_t)p.mask[tile * POLICY_TILE * 26 + i];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                // the env's observation row as bf16 pairs (exact: -24 .. 127), zero beyond D; its legal-action bits
+                const int8_t *orow = s_obs + row * D;
 #pragma unroll
                 for (int g = 0; g < POLICY_K1 / 32; ++g) {
                     uint32_t w[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int k = 32 * g + 2 * j;
-                        const float x0 = (valid && k < D) ? (float)row[k] : 0.f;
-                        const float x1 = (valid && k + 1 < D) ? (float)row[k + 1] : 0.f;
+                        const float x0 = (valid && k < D) ? (float)orow[k] : 0.f;
+                        const float x1 = (valid && k + 1 < D) ? (float)orow[k + 1] : 0.f;
                         w[j] = pack_bf16x2(x0, x1);
                     }
                     tc_st16(R2 + 16 * g, w);
                 }
                 if (valid) {
-                    const int8_t *mr = s_mask + tid * 26;
+                    const int8_t *mr = s_mask + row * 26;
 #pragma unroll
                     for (int a = 0; a < 26; ++a) legal |= (mr[a] != 0 ? 1u : 0u) << a;
                 }
+                tc_wait_st();
             }
-            tc_wait_st();
             tc_fence_before();
             mbar_arrive(bar_a);
-            // every row of the tile has been read: the next tile's rows may land
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 0 && tile + gridDim.x < n_tiles && tile_is_bulk(tile + gridDim.x)) issue_tile(tile + gridDim.x);
+            if (group == 0) {
+                // every row of the tile has been read: the next tile's rows may land
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid == 0 && tile + gridDim.x < n_tiles && tile_is_bulk(tile + gridDim.x)) issue_tile(tile + gridDim.x);
+            }
 
             mbar_wait(bar_d, ph_d);  // D1 = x W1^T
             ph_d ^= 1u;
             tc_fence_after();
-            hidden_epilogue(R1, R1, s_b1, (p.dbg1 && valid) ? p.dbg1 + e * POLICY_HIDDEN : nullptr);
-            tc_fence_before();
-            mbar_arrive(bar_a);
+            hidden_epilogue(R1, group, s_b1, (p.dbg1 && valid) ? p.dbg1 + e * POLICY_HIDDEN : nullptr, bar_h);
 
             mbar_wait(bar_d, ph_d);  // D2 = h1 W2^T
             ph_d ^= 1u;
             tc_fence_after();
-            hidden_epilogue(R2, R2, s_b2, (p.dbg2 && valid) ? p.dbg2 + e * POLICY_HIDDEN : nullptr);
-            tc_fence_before();
-            mbar_arrive(bar_a);
+            hidden_epilogue(R2, group, s_b2, (p.dbg2 && valid) ? p.dbg2 + e * POLICY_HIDDEN : nullptr, bar_h);
 
             mbar_wait(bar_d, ph_d);  // D3 = h2 W3^T
             ph_d ^= 1u;
             tc_fence_after();
-            uint32_t v[32];
-            tc_ld32(R1 + 128u, v);
-            tc_wait_ld();
-            if (valid) {
-                if (p.value) {
-                    p.value[e] = __uint_as_float(v[0]) + s_b3[0];
-                } else {
-                    float l[26];
+            if (group == 0) {
+                uint32_t v[32];
+                tc_ld32(R1 + POL_D3_COL, v);
+                tc_wait_ld();
+                if (valid) {
+                    if (p.value) {
+                        p.value[e] = __uint_as_float(v[0]) + s_b3[0];
+                    } else {
+                        float l[26];
 #pragma unroll
-                    for (int a = 0; a < 26; ++a) l[a] = __uint_as_float(v[a]) + s_b3[a];
-                    if (p.logits) {
+                        for (int a = 0; a < 26; ++a) l[a] = __uint_as_float(v[a]) + s_b3[a];
+                        if (p.logits) {
 #pragma unroll
-                        for (int a = 0; a < 26; ++a) p.logits[e * 26 + a] = l[a];
-                    }
-                    if (p.actions) {
-                        if (legal == 0) {  // cannot happen for a live env; keep the step well defined
-                            p.actions[e] = 255;
-                            if (p.logp) p.logp[e] = 0.f;
-                            if (p.entropy) p.entropy[e] = 0.f;
-                        } else {
-                            int act;
-                            float lp, ent;
-                            sample_masked(l, legal, p.seed, p.first_env + (unsigned long long)e, p.t, act, lp, ent);
-                            p.actions[e] = (uint8_t)act;
-                            if (p.logp) p.logp[e] = lp;
-                            if (p.entropy) p.entropy[e] = ent;
+                            for (int a = 0; a < 26; ++a) p.logits[e * 26 + a] = l[a];
+                        }
+                        if (p.actions) {
+                            if (legal == 0) {  // cannot happen for a live env; keep the step well defined
+                                p.actions[e] = 255;
+                                if (p.logp) p.logp[e] = 0.f;
+                                if (p.entropy) p.entropy[e] = 0.f;
+                            } else {
+                                int act;
+                                float lp, ent;
+                                sample_masked(l, legal, p.seed, p.first_env + (unsigned long long)e, p.t, act, lp, ent);
+                                p.actions[e] = (uint8_t)act;
+                                if (p.logp) p.logp[e] = lp;
+                                if (p.entropy) p.entropy[e] = ent;
+                            }
                         }
                     }
                 }
             }
-            tc_fence_before();  // the D3 / h2 columns are rewritten by the next tile's operand store and MMA
+            // both groups pass here before they arrive on bar_a for the next tile, whose first MMA overwrites D3 / h1
         }
     } else {
-        // ---- the MMA warp: 6 + 16 + 16 tcgen05.mma per tile, issued by lane 0; A from tensor memory, B from shared memory
+        // ---- the MMA warp (warp 8): 6 + 16 + 16 tcgen05.mma per tile, issued by lane 0; A from tensor memory, B from shared memory
         constexpr uint32_t I256 = idesc_bf16(POLICY_TILE, POLICY_HIDDEN), I32 = idesc_bf16(POLICY_TILE, POL_N3);
         constexpr uint32_t KSTEP_H = 2u * (POLICY_HIDDEN / 8) * 128u;  // bytes between K = 16 slices of W1 / W2
         constexpr uint32_t KSTEP_3 = 2u * (POL_N3 / 8) * 128u;
-        uint32_t ph_a = 0;
+        uint32_t ph_a = 0, ph_h = 0;
         mbar_wait(bar_w, 0);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(bar_a, ph_a);
@@ -328,31 +356,40 @@ __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_con
                 tc_commit(bar_d);
             }
             __syncwarp();
-            mbar_wait(bar_a, ph_a);
-            ph_a ^= 1u;
-            tc_fence_after();
-            if (lane == 0) {
+            // layers 2 and 3 run behind the epilogue that produces their operand: two MMAs (K = 32) per announced chunk
+#pragma unroll 1
+            for (uint32_t c = 0; c < 8; ++c) {
+                mbar_wait(bar_h + 8 * c, ph_h);
+                tc_fence_after();
+                if (lane == 0) {
 #pragma unroll
-                for (uint32_t k = 0; k < POLICY_HIDDEN / 16; ++k)
-                    tc_mma_ts(tmem + 256u, tmem + 8u * k, b_desc(sm + OFF_W2 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
-                tc_commit(bar_d);
+                    for (uint32_t k = 2 * c; k < 2 * c + 2; ++k)
+                        tc_mma_ts(tmem + 256u, tmem + hidden_col(c) + 8u * (k & 1u),
+                                  b_desc(sm + OFF_W2 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
+                    if (c == 7) tc_commit(bar_d);
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            mbar_wait(bar_a, ph_a);
-            ph_a ^= 1u;
-            tc_fence_after();
-            if (lane == 0) {
+            ph_h ^= 1u;
+#pragma unroll 1
+            for (uint32_t c = 0; c < 8; ++c) {
+                mbar_wait(bar_h + 8 * c, ph_h);
+                tc_fence_after();
+                if (lane == 0) {
 #pragma unroll
-                for (uint32_t k = 0; k < POLICY_HIDDEN / 16; ++k)
-                    tc_mma_ts(tmem + 128u, tmem + 256u + 8u * k, b_desc(sm + OFF_W3 + k * KSTEP_3, POL_N3), I32, k);
-                tc_commit(bar_d);
+                    for (uint32_t k = 2 * c; k < 2 * c + 2; ++k)
+                        tc_mma_ts(tmem + POL_D3_COL, tmem + 256u + hidden_col(c) + 8u * (k & 1u),
+                                  b_desc(sm + OFF_W3 + k * KSTEP_3, POL_N3), I32, k);
+                    if (c == 7) tc_commit(bar_d);
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            ph_h ^= 1u;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp == POL_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 // fp32 torch.nn.Linear weights (W[out][in], row-major) -> the kernel's shared-memory image
