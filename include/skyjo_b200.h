@@ -302,6 +302,11 @@ int skyjo_policy_sample(SkyjoHandle *h, const void *packed_dev, uint64_t sample_
 int skyjo_policy_value(SkyjoHandle *h, const void *packed_dev, float *value_dev, void *stream);
 int skyjo_policy_debug(SkyjoHandle *h, const void *packed_dev, float *pre1_dev, float *pre2_dev, float *logits_dev,
                        void *stream);
+/* Measurement aid: skyjo_policy_sample (seed 0) that also records clock64() at every hand-over between the three
+ * roles of the kernel's first CTA into trace_dev, int64[3][skyjo_policy_trace_len()] zero-filled by the caller
+ * (hidden-epilogue team, staging / sampling team, MMA warp); decoded by tools/policy_trace.py. */
+int skyjo_policy_trace(SkyjoHandle *h, const void *packed_dev, uint8_t *actions_dev, int64_t *trace_dev, void *stream);
+int skyjo_policy_trace_len(void);
 /* Closes the running refill window and makes `stream` wait for the library's internal streams:
  * work queued on `stream` afterwards may read or overwrite the state buffer (checkpointing). */
 int skyjo_quiesce(SkyjoHandle *h, void *stream);

@@ -37,7 +37,7 @@ EXPORTS = [
     "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs", "skyjo_stats_allreduce",
     "skyjo_host_reshuffle", "skyjo_set_env_ranges", "skyjo_stats_allreduce_async", "skyjo_stats_allreduce_wait",
     "skyjo_host_simd_level", "skyjo_host_wire_share", "skyjo_policy_packed_bytes", "skyjo_policy_pack",
-    "skyjo_policy_sample", "skyjo_policy_value", "skyjo_policy_debug",
+    "skyjo_policy_sample", "skyjo_policy_value", "skyjo_policy_debug", "skyjo_policy_trace", "skyjo_policy_trace_len",
 ]
 
 
@@ -145,6 +145,8 @@ def load():
         "skyjo_policy_sample": (i32, [vp, vp, u64, vp, vp, vp, vp, vp]),
         "skyjo_policy_value": (i32, [vp, vp, vp, vp]),
         "skyjo_policy_debug": (i32, [vp, vp, vp, vp, vp, vp]),
+        "skyjo_policy_trace": (i32, [vp, vp, vp, vp, vp]),
+        "skyjo_policy_trace_len": (i32, []),
         "skyjo_quiesce": (i32, [vp, vp]),
         "skyjo_export_debug": (i32, [vp, i64, i64, vp, vp]),
         "skyjo_check": (i32, [vp, vp]),

@@ -1234,6 +1234,17 @@ int skyjo_policy_debug(SkyjoHandle *h, const void *packed_dev, float *pre1_dev, 
     return policy_launch(h, packed_dev, p, stream);
 }
 
+int skyjo_policy_trace(SkyjoHandle *h, const void *packed_dev, uint8_t *actions_dev, int64_t *trace_dev, void *stream) {
+    if (!actions_dev || !trace_dev) return fail(SKYJO_E_INVALID, "null argument");
+    PolicyParams p;
+    memset(&p, 0, sizeof(p));
+    p.actions = actions_dev;
+    p.trace = (long long *)trace_dev;
+    return policy_launch(h, packed_dev, p, stream);
+}
+
+int skyjo_policy_trace_len(void) { return POLICY_TRACE_LEN; }
+
 int skyjo_quiesce(SkyjoHandle *h, void *stream) {
     if (!h) return fail(SKYJO_E_INVALID, "null handle");
     CU(cudaSetDevice(h->device));

@@ -13,15 +13,13 @@
 //     and the obs / mask rows of the tile being started (1-D TMA bulk copies, one tile ahead);
 //   * tensor memory (all 512 columns x 128 lanes) holds every activation: an env is a TMEM lane.  The A operand
 //     of each product is read FROM TENSOR MEMORY (tcgen05.mma with a TMEM A address), so activations never touch
-//     shared memory: warps 0-3 (one thread per env) convert the obs row to bf16 and tcgen05.st it; after each hidden
-//     layer warps 0-7 (two per scheduler, so that one's TMEM round trips hide behind the other's tanh; warps w and
-//     w + 4 own the same 32 lanes and one half of the 256 hidden units each) read the fp32 accumulators with
-//     tcgen05.ld, add the bias, apply tanh, pack to bf16 and store them back in place (a 32-column chunk of fp32
-//     compacts into 16 columns of bf16 pairs at the start of its half), announcing every chunk on an mbarrier;
-//   * warp 8, lane 0 issues the MMAs: 6 + 16 + 16 per tile -- those of layers 2 and 3 two at a time (K = 32) behind
-//     the epilogue chunk that produces their operand -- and tcgen05.commit's each layer onto an mbarrier.
-// Column map: R1 = [0, 256): D1 -> h1 as bf16 in [0, 64) and [128, 192); D3 (logits) in [64, 96).
-//             R2 = [256, 512): obs as bf16 in [256, 304) -> D2 -> h2 as bf16 in [256, 320) and [384, 448).
+//     shared memory: one thread per env converts the obs row to bf16 and tcgen05.st's it; after each hidden layer
+//     one thread per env reads the fp32 accumulators with tcgen05.ld, adds the bias, applies tanh, packs to bf16 and
+//     stores them back in place (a 32-column chunk of fp32 compacts into 16 columns of bf16 pairs), announcing
+//     every chunk on an mbarrier so that the next layer's MMAs over that K-chunk start at once;
+//   * one team of warps does nothing but the hidden epilogues (the critical path), a second team stages the next
+//     tile's operand and samples the previous tile's actions meanwhile, one more warp issues the MMAs (6 + 16 + 16
+//     per tile); the two halves of tensor memory swap roles from tile to tile (column map at policy_kernel).
 // Roofline: 2 x (96 + 256) x 256 + 2 x 256 x 32 = 196 608 FLOP per env as issued (178 688 useful) on the tensor cores,
 // and 512 tanh per env on the SFUs (MUFU.TANH: 16 XU-pipe cycles per warp instruction), which is the longer of the
 // two per tile: 57 us per 2^18 envs at 1.965 GHz against 22 us of MMA time; see DESIGN.md.
@@ -35,10 +33,18 @@
 
 namespace skyjo {
 
-constexpr int POL_THREADS = 288;  // warps 0-7: two threads per env (TMEM lane = tid & 127), half of the hidden units each;
-                                  // warp 8: MMA issue
-constexpr int POL_MMA_WARP = 8;
-constexpr uint32_t POL_D3_COL = 64;  // logits accumulate in columns [64, 96) of R1
+// Team H has one or two warps per scheduler (with two, warps w and w + 4 share the 32 lanes of quadrant w and take
+// one half of the 256 hidden units each).  Measured (2^18 envs, tools/policy_kernel_bench.py): see DESIGN.md.
+#ifndef SKYJO_POLICY_HGROUPS
+#define SKYJO_POLICY_HGROUPS 1
+#endif
+constexpr int POL_HGROUPS = SKYJO_POLICY_HGROUPS;
+constexpr uint32_t POL_D3_COL = POL_HGROUPS == 1 ? 128u : 64u;  // the logits accumulate in 32 columns of P clear of h1 and of x(j+1)
+constexpr int POL_H_WARPS = 4 * POL_HGROUPS;       // warps [0, POL_H_WARPS): hidden epilogues
+constexpr int POL_S_WARP0 = POL_H_WARPS;           // 4 warps: operand staging + sampling (one thread per env = TMEM lane)
+constexpr int POL_MMA_WARP = POL_H_WARPS + 4;      // MMA issue
+constexpr int POL_THREADS = 32 * (POL_MMA_WARP + 1);
+
 constexpr int POL_N3 = 32;        // 26 logits (or 1 value) padded to an MMA N
 constexpr uint32_t OFF_W1 = 0;
 constexpr uint32_t OFF_W2 = OFF_W1 + POLICY_K1 * POLICY_HIDDEN * 2;
@@ -51,7 +57,7 @@ static_assert(PACKED_BYTES == POLICY_PACKED_BYTES, "skyjo_policy.h out of date")
 constexpr uint32_t OFF_OBS = PACKED_BYTES;                                   // 128 rows of up to POLICY_MAX_OBS bytes
 constexpr uint32_t OFF_MASK = OFF_OBS + ((POLICY_TILE * POLICY_MAX_OBS + 127) / 128) * 128;
 constexpr uint32_t OFF_BAR = OFF_MASK + POLICY_TILE * 26;                    // 3328 = 26 * 128
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;  // 4 + 8 mbarriers, the TMEM base address
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 192;  // 8 + 8 mbarriers, the TMEM base address
 static_assert(SMEM_BYTES <= 227 * 1024, "policy kernel shared memory");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -121,10 +127,6 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {  // element 2j in the low half
-    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t *>(&p);
-}
 
 // K-major operand in the canonical no-swizzle layout: element (r, k) of an R x K matrix at
 //   ((k / 8) * (R / 8) + r / 8) * 128 + (r % 8) * 16 + (k % 8) * 2        bytes,
@@ -145,30 +147,45 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-// tanh on the SFUs.  Measured on B200 (ncu, profiles/r2_policy_*): MUFU.TANH occupies the XU pipe for 16 cycles per
-// warp instruction (half the rate of ex2 / rcp), the packed bf16x2 form is issued as two MUFU.TANH.BF16, and
-// 1 - 2 / (exp2(2 log2(e) a) + 1) through ex2 + rcp costs the same 16 pipe cycles plus three more issue slots
-// (152 us against 112 us per 2^18 envs): 512 tanh per env bound this kernel at 2^18 x 512 x 16 / (32 x 4 x 148)
-// cycles = 57 us at 1.965 GHz, about three times its tensor-core time.
-__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
-    uint32_t y;
-    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+// tanh on the SFUs, everything else off them.  Measured on B200 (ncu, profiles/r2_policy_*): the XU pipe (MUFU,
+// and every int <-> float / float -> bf16 conversion: I2F, F2FP) is what bounds this kernel.  MUFU.TANH occupies it
+// for 16 cycles per warp instruction (half the rate of ex2 / rcp; tanh.approx.bf16x2 is issued as two of them, and
+// 1 - 2 / (exp2(2 log2(e) a) + 1) through ex2 + rcp costs the same 16 cycles plus three issue slots), a conversion
+// for 8.  So the conversions are done on the ALU instead: an activation is rounded to bf16 by adding 0x8000 to its
+// fp32 bits and keeping the high half (PRMT packs two), an int8 observation becomes a float through the 1.5 x 2^23
+// trick and is exact in its high half.  Floor: 512 tanh per env x 16 cycles / 32 lanes / 4 schedulers per SM
+// = 8192 cycles per 128-env tile = 58 us per 2^18 envs at 1.965 GHz, 2.6 times the kernel's tensor-core time.
+__device__ __forceinline__ float tanh_f32(float x) {
+#ifdef SKYJO_POLICY_EXP_NOTANH  // timing experiment only: what the kernel costs without its SFU work
+    return x;
+#else
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
+}
+// two fp32 -> one word of two bf16 (element 2j in the low half), round half up on the magnitude bits
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+// int8 -> fp32 without I2F: 0x4B400000 is 1.5 x 2^23, whose unit in the last place is 1
+__device__ __forceinline__ float int8_to_float(int v) { return __uint_as_float(0x4B400000u + (uint32_t)v) - 12582912.0f; }
+
+// column (relative to its 256-column region) of the bf16 pairs of hidden units [32 c, 32 c + 32): a chunk of 32
+// fp32 columns compacts in place to 16 columns -- chunks 0-3 to the start of the first half of the region, chunks
+// 4-7 to the start of the second half, so that each half of team H only overwrites columns it has read itself
+__host__ __device__ constexpr uint32_t hidden_col(uint32_t c) {
+    return (POL_HGROUPS == 1 || c < 4) ? 16u * c : 128u + 16u * (c - 4u);
 }
 
-// column (relative to its 256-column region) of the bf16 pairs of hidden units [32 c, 32 c + 32): chunks 0-3 compact
-// to the start of the first half, chunks 4-7 to the start of the second half, each over columns its own half of
-// the epilogue team has already read
-__host__ __device__ constexpr uint32_t hidden_col(uint32_t c) { return c < 4 ? 16u * c : 128u + 16u * (c - 4u); }
-
 // tanh(acc + bias) of one half (group 0: hidden units 0..127, group 1: 128..255) of the 256 fp32 columns of
-// `region`, packed to bf16 pairs in place (same lanes).  The sums are rounded to bf16 before the tanh
-// (tanh.approx.bf16x2: the result is the packed operand itself); the next layer's MMAs over K-chunk c start as soon
-// as all 128 rows have announced it on bar_h[c].
+// `region`, packed to bf16 pairs in place (same lanes); the next layer's MMAs over K-chunk c start as soon as all
+// 128 rows have announced it on bar_h[c].
 __device__ __forceinline__ void hidden_epilogue(uint32_t region, int group, const float *s_bias, float *dbg_row,
                                                 uint32_t bar_h) {
 #pragma unroll 1
-    for (int c = 4 * group; c < 4 * group + 4; ++c) {
+    constexpr int PER = 8 / POL_HGROUPS;
+    for (int c = PER * group; c < PER * group + PER; ++c) {
         uint32_t v[32];
         tc_ld32(region + 32 * c, v);
         tc_wait_ld();
@@ -180,7 +197,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t region, int group, cons
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float2 b = *reinterpret_cast<const float2 *>(s_bias + 32 * c + 2 * j);
-            w[j] = tanh_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]) + b.x, __uint_as_float(v[2 * j + 1]) + b.y));
+            w[j] = pack_bf16x2_alu(tanh_f32(__uint_as_float(v[2 * j]) + b.x), tanh_f32(__uint_as_float(v[2 * j + 1]) + b.y));
         }
         tc_st16(region + hidden_col(c), w);
         tc_wait_st();
@@ -189,14 +206,29 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t region, int group, cons
     }
 }
 
+// Three roles, one tile (128 envs) after the other per CTA, two tiles in flight:
+//   team H (4 or 8 warps)  the two hidden epilogues of every tile -- the critical path, kept busy back to back;
+//   team S (4 warps)       stages the NEXT tile's observation rows into tensor memory while H is in its second epilogue,
+//                          then samples the CURRENT tile's actions from the logits while H has moved on to the next tile;
+//   one more warp, lane 0  issues the MMAs.
+// Both teams see all 128 TMEM lanes (a warp reaches lanes 32 (warp % 4) ..).  The two 256-column halves of tensor
+// memory swap roles from tile to tile (j = the CTA's tile counter, P = primary = j odd ? [256, 512) : [0, 256),
+// Q = the other half):
+//   x(j) as bf16 in Q[192, 240)  ->  D1(j) in P  -> h1(j) in P[0, 128) (two H groups: P[0, 64) + P[128, 192))
+//   ->  D2(j) in Q  ->  h2(j) likewise in Q  ->  D3(j) (logits) in P[D3], D3 = 128 (two groups: 64)
+// x(j+1) is staged into Q(j+1)[192, 240) = P(j)[192, 240) once H has compacted D1(j) (bar_e); D1(j+1) lands in
+// P(j+1) = Q(j) once MMA3(j) has read h2(j) from it (the MMA warp waits for its own bar_d3); D2(j+1) overwrites
+// D3(j) in Q(j+1) = P(j) once S has pulled the logits into registers (bar_c).
 __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_constant__ PolicyParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sm = smem_u32(smem);
-    // bar_w: weights landed; bar_in: the tile's obs / mask rows landed; bar_a: the 128 obs rows are in tensor memory;
-    // bar_h[c]: chunk c (32 of the 256 hidden units) of the current hidden layer is in tensor memory as bf16;
-    // bar_d: the MMAs of a layer have completed (tcgen05.commit)
-    const uint32_t bar_w = sm + OFF_BAR, bar_in = bar_w + 8, bar_a = bar_w + 16, bar_d = bar_w + 24, bar_h = bar_w + 32;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 96);
+    // bar_w  weights landed (tx)                       bar_in  a tile's obs / mask rows landed (tx)
+    // bar_a  S -> MMA: x(j) is in tensor memory (128)   bar_d1 / bar_d2 / bar_d3  MMA -> H / H / S: a layer's MMAs completed
+    // bar_h[c]  H -> MMA: chunk c of the current hidden layer is in tensor memory (128)
+    // bar_e  H -> S: D1(j) has been compacted (256)     bar_c  S -> MMA: the logits of tile j are in registers (128)
+    const uint32_t bar_w = sm + OFF_BAR, bar_in = bar_w + 8, bar_a = bar_w + 16, bar_d1 = bar_w + 24, bar_d2 = bar_w + 32,
+                   bar_d3 = bar_w + 40, bar_e = bar_w + 48, bar_c = bar_w + 56, bar_h = bar_w + 64;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_tiles = (p.B + POLICY_TILE - 1) / POLICY_TILE;
     const int D = p.D;
@@ -204,12 +236,16 @@ __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_con
     if (tid == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_in, 1);
-        mbar_init(bar_a, 2 * POLICY_TILE);  // both halves of the epilogue team have left the previous tile
-        mbar_init(bar_d, 1);
+        mbar_init(bar_a, POLICY_TILE);
+        mbar_init(bar_d1, 1);
+        mbar_init(bar_d2, 1);
+        mbar_init(bar_d3, 1);
+        mbar_init(bar_e, POL_HGROUPS * POLICY_TILE);
+        mbar_init(bar_c, POLICY_TILE);
         for (int c = 0; c < 8; ++c) mbar_init(bar_h + 8 * c, POLICY_TILE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == POL_MMA_WARP) {  // one warp allocates all of tensor memory (one CTA per SM: 200 KB of shared memory)
+    if (warp == POL_MMA_WARP) {  // one warp allocates all of tensor memory (one CTA per SM: 210 KB of shared memory)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -226,166 +262,207 @@ __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_con
         bulk_load(sm + OFF_OBS, p.obs + tile * POLICY_TILE * D, ob, bar_in);
         bulk_load(sm + OFF_MASK, p.mask + tile * POLICY_TILE * 26, mb, bar_in);
     };
+    const long long first_tile = blockIdx.x, stride = gridDim.x;
+    // timeline marks of CTA 0 (one lane per role): clock64() at every hand-over, decoded by tools/policy_trace.py
+    long long *trace_role = nullptr;
+    int trace_n = 0;
+    auto mark = [&]() {
+        if (trace_role && trace_n < POLICY_TRACE_LEN) trace_role[trace_n++] = clock64();
+    };
 
-    if (tid == 0) {
+    if (tid == 0) {  // the weight image, once per CTA (L2-resident after the first CTAs)
         mbar_expect_tx(bar_w, PACKED_BYTES);
         for (uint32_t off = 0; off < PACKED_BYTES; off += 32768u) {
             const uint32_t n = PACKED_BYTES - off < 32768u ? PACKED_BYTES - off : 32768u;
             bulk_load(sm + off, p.packed + off, n, bar_w);
         }
-        if ((long long)blockIdx.x < n_tiles && tile_is_bulk(blockIdx.x)) issue_tile(blockIdx.x);
     }
 
-    if (warp < POL_MMA_WARP) {
-        // ---- the epilogue team: row = TMEM lane = tid & 127; group 0 (warps 0-3) also stages the operand and samples ---
+    if (warp < POL_H_WARPS) {
+        // ---- team H: the hidden epilogues ------------------------------------------------------------------------
         const int group = warp >> 2, row = tid & (POLICY_TILE - 1);
         const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-        const uint32_t R1 = tmem + lane_base, R2 = tmem + lane_base + 256u;
         const float *s_b1 = reinterpret_cast<const float *>(smem + OFF_B1);
         const float *s_b2 = reinterpret_cast<const float *>(smem + OFF_B2);
+        if (p.trace && blockIdx.x == 0 && tid == 0) trace_role = p.trace;
+        mbar_wait(bar_w, 0);
+        uint32_t j = 0;
+        for (long long tile = first_tile; tile < n_tiles; tile += stride, ++j) {
+            const uint32_t P = tmem + lane_base + ((j & 1u) ? 256u : 0u), Q = tmem + lane_base + ((j & 1u) ? 0u : 256u);
+            const long long e = tile * POLICY_TILE + row;
+            const bool valid = e < p.B;
+            mark();                     // H0: waiting for D1
+            mbar_wait(bar_d1, j & 1u);  // D1 = x W1^T
+            tc_fence_after();
+            mark();                     // H1: first epilogue starts
+            hidden_epilogue(P, group, s_b1, (p.dbg1 && valid) ? p.dbg1 + e * POLICY_HIDDEN : nullptr, bar_h);
+            mbar_arrive(bar_e);         // (ordered behind the tcgen05 fence of the last chunk)
+            mark();                     // H2: first epilogue done, waiting for D2
+            mbar_wait(bar_d2, j & 1u);  // D2 = h1 W2^T
+            tc_fence_after();
+            mark();                     // H3: second epilogue starts
+            hidden_epilogue(Q, group, s_b2, (p.dbg2 && valid) ? p.dbg2 + e * POLICY_HIDDEN : nullptr, bar_h);
+            mark();                     // H4: second epilogue done
+        }
+    } else if (warp < POL_MMA_WARP) {
+        // ---- team S: operand staging one tile ahead, output epilogue one tile behind -------------------------------
+        const int row = tid - POL_HGROUPS * POLICY_TILE;
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
         const float *s_b3 = reinterpret_cast<const float *>(smem + OFF_B3);
         const int8_t *s_obs = reinterpret_cast<const int8_t *>(smem + OFF_OBS);
         const int8_t *s_mask = reinterpret_cast<const int8_t *>(smem + OFF_MASK);
-        uint32_t ph_in = 0, ph_d = 0;
-        mbar_wait(bar_w, 0);
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t ph_in = 0;
+        if (row == 0 && first_tile < n_tiles && tile_is_bulk(first_tile)) issue_tile(first_tile);
+
+        // x(j) of `tile` -> Q(j)[192, 240) as bf16 pairs (exact: -24 .. 127; zero beyond D); returns the row's legal bits
+        auto stage = [&](long long tile, uint32_t j) -> uint32_t {
             const long long e = tile * POLICY_TILE + row;
             const bool valid = e < p.B;
-            uint32_t legal = 0;
-            if (group == 0) {
-                if (tile_is_bulk(tile)) {
-                    mbar_wait(bar_in, ph_in);
-                    ph_in ^= 1u;
-                } else {
-                    const long long rows = p.B - tile * POLICY_TILE < POLICY_TILE ? p.B - tile * POLICY_TILE : POLICY_TILE;
-                    for (int i = row; i < rows * D; i += POLICY_TILE) smem[OFF_OBS + i] = (uint8_t)p.obs[tile * POLICY_TILE * D + i];
-                    for (int i = row; i < rows * 26; i += POLICY_TILE) smem[OFF_MASK + i] = (uint8_t)p.mask[tile * POLICY_TILE * 26 + i];
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
-                // the env's observation row as bf16 pairs (exact: -24 .. 127), zero beyond D; its legal-action bits
-                const int8_t *orow = s_obs + row * D;
-#pragma unroll
-                for (int g = 0; g < POLICY_K1 / 32; ++g) {
-                    uint32_t w[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int k = 32 * g + 2 * j;
-                        const float x0 = (valid && k < D) ? (float)orow[k] : 0.f;
-                        const float x1 = (valid && k + 1 < D) ? (float)orow[k + 1] : 0.f;
-                        w[j] = pack_bf16x2(x0, x1);
-                    }
-                    tc_st16(R2 + 16 * g, w);
-                }
-                if (valid) {
-                    const int8_t *mr = s_mask + row * 26;
-#pragma unroll
-                    for (int a = 0; a < 26; ++a) legal |= (mr[a] != 0 ? 1u : 0u) << a;
-                }
-                tc_wait_st();
+            if (tile_is_bulk(tile)) {
+                mbar_wait(bar_in, ph_in);
+                ph_in ^= 1u;
+            } else {
+                const long long rows = p.B - tile * POLICY_TILE < POLICY_TILE ? p.B - tile * POLICY_TILE : POLICY_TILE;
+                for (int i = row; i < rows * D; i += POLICY_TILE) smem[OFF_OBS + i] = (uint8_t)p.obs[tile * POLICY_TILE * D + i];
+                for (int i = row; i < rows * 26; i += POLICY_TILE) smem[OFF_MASK + i] = (uint8_t)p.mask[tile * POLICY_TILE * 26 + i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+            const uint32_t Qx = tmem + lane_base + ((j & 1u) ? 0u : 256u) + 192u;
+            const int8_t *orow = s_obs + row * D;
+#pragma unroll
+            for (int g = 0; g < POLICY_K1 / 32; ++g) {
+                uint32_t w[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int k = 32 * g + 2 * q;
+                    const float x0 = (valid && k < D) ? int8_to_float(orow[k]) : 0.f;
+                    const float x1 = (valid && k + 1 < D) ? int8_to_float(orow[k + 1]) : 0.f;
+                    w[q] = __byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632);  // exact in bf16
+                }
+                tc_st16(Qx + 16 * g, w);
+            }
+            uint32_t legal = 0;
+            if (valid) {
+                const int8_t *mr = s_mask + row * 26;
+#pragma unroll
+                for (int a = 0; a < 26; ++a) legal |= (mr[a] != 0 ? 1u : 0u) << a;
+            }
+            tc_wait_st();
             tc_fence_before();
             mbar_arrive(bar_a);
-            if (group == 0) {
-                // every row of the tile has been read: the next tile's rows may land
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (tid == 0 && tile + gridDim.x < n_tiles && tile_is_bulk(tile + gridDim.x)) issue_tile(tile + gridDim.x);
+            // every row of the tile has been read: the next tile's rows may land
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (row == 0 && tile + stride < n_tiles && tile_is_bulk(tile + stride)) issue_tile(tile + stride);
+            return legal;
+        };
+
+        if (p.trace && blockIdx.x == 0 && row == 0) trace_role = p.trace + POLICY_TRACE_LEN;
+        mbar_wait(bar_w, 0);  // b3
+        uint32_t legal = 0, j = 0;
+        if (first_tile < n_tiles) legal = stage(first_tile, 0);
+        for (long long tile = first_tile; tile < n_tiles; tile += stride, ++j) {
+            uint32_t legal_next = 0;
+            mark();                        // S0: waiting for the staging slot
+            if (tile + stride < n_tiles) {
+                mbar_wait(bar_e, j & 1u);  // D1(j) compacted: P(j)[192, 240) = Q(j+1)[192, 240) is free
+                tc_fence_after();
+                mark();                    // S1: staging x(j+1)
+                legal_next = stage(tile + stride, j + 1);
+            } else {
+                mark();
             }
-
-            mbar_wait(bar_d, ph_d);  // D1 = x W1^T
-            ph_d ^= 1u;
+            const long long e = tile * POLICY_TILE + row;
+            const bool valid = e < p.B;
+            mark();                        // S2: staged, waiting for the logits
+            mbar_wait(bar_d3, j & 1u);  // D3 = h2 W3^T
             tc_fence_after();
-            hidden_epilogue(R1, group, s_b1, (p.dbg1 && valid) ? p.dbg1 + e * POLICY_HIDDEN : nullptr, bar_h);
-
-            mbar_wait(bar_d, ph_d);  // D2 = h1 W2^T
-            ph_d ^= 1u;
-            tc_fence_after();
-            hidden_epilogue(R2, group, s_b2, (p.dbg2 && valid) ? p.dbg2 + e * POLICY_HIDDEN : nullptr, bar_h);
-
-            mbar_wait(bar_d, ph_d);  // D3 = h2 W3^T
-            ph_d ^= 1u;
-            tc_fence_after();
-            if (group == 0) {
-                uint32_t v[32];
-                tc_ld32(R1 + POL_D3_COL, v);
-                tc_wait_ld();
-                if (valid) {
-                    if (p.value) {
-                        p.value[e] = __uint_as_float(v[0]) + s_b3[0];
-                    } else {
-                        float l[26];
+            mark();                        // S3: sampling
+            uint32_t v[32];
+            tc_ld32(tmem + lane_base + ((j & 1u) ? 256u : 0u) + POL_D3_COL, v);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_c);
+            if (valid) {
+                if (p.value) {
+                    p.value[e] = __uint_as_float(v[0]) + s_b3[0];
+                } else {
+                    float l[26];
 #pragma unroll
-                        for (int a = 0; a < 26; ++a) l[a] = __uint_as_float(v[a]) + s_b3[a];
-                        if (p.logits) {
+                    for (int a = 0; a < 26; ++a) l[a] = __uint_as_float(v[a]) + s_b3[a];
+                    if (p.logits) {
 #pragma unroll
-                            for (int a = 0; a < 26; ++a) p.logits[e * 26 + a] = l[a];
-                        }
-                        if (p.actions) {
-                            if (legal == 0) {  // cannot happen for a live env; keep the step well defined
-                                p.actions[e] = 255;
-                                if (p.logp) p.logp[e] = 0.f;
-                                if (p.entropy) p.entropy[e] = 0.f;
-                            } else {
-                                int act;
-                                float lp, ent;
-                                sample_masked(l, legal, p.seed, p.first_env + (unsigned long long)e, p.t, act, lp, ent);
-                                p.actions[e] = (uint8_t)act;
-                                if (p.logp) p.logp[e] = lp;
-                                if (p.entropy) p.entropy[e] = ent;
-                            }
+                        for (int a = 0; a < 26; ++a) p.logits[e * 26 + a] = l[a];
+                    }
+                    if (p.actions) {
+                        if (legal == 0) {  // cannot happen for a live env; keep the step well defined
+                            p.actions[e] = 255;
+                            if (p.logp) p.logp[e] = 0.f;
+                            if (p.entropy) p.entropy[e] = 0.f;
+                        } else {
+                            int act;
+                            float lp, ent;
+                            sample_masked(l, legal, p.seed, p.first_env + (unsigned long long)e, p.t, act, lp, ent);
+                            p.actions[e] = (uint8_t)act;
+                            if (p.logp) p.logp[e] = lp;
+                            if (p.entropy) p.entropy[e] = ent;
                         }
                     }
                 }
             }
-            // both groups pass here before they arrive on bar_a for the next tile, whose first MMA overwrites D3 / h1
+            legal = legal_next;
+            mark();                        // S4: sampled
         }
     } else {
-        // ---- the MMA warp (warp 8): 6 + 16 + 16 tcgen05.mma per tile, issued by lane 0; A from tensor memory, B from shared memory
+        // ---- the MMA warp: 6 + 16 + 16 tcgen05.mma per tile, all issued by lane 0; A from tensor memory, B from shared
+        // memory.  The other lanes wait at the __syncwarp below.  Chunks are taken in the order the two halves of team
+        // H produce them (0, 4, 1, 5, ...), so that the MMAs of a layer end right behind its epilogue.
         constexpr uint32_t I256 = idesc_bf16(POLICY_TILE, POLICY_HIDDEN), I32 = idesc_bf16(POLICY_TILE, POL_N3);
         constexpr uint32_t KSTEP_H = 2u * (POLICY_HIDDEN / 8) * 128u;  // bytes between K = 16 slices of W1 / W2
         constexpr uint32_t KSTEP_3 = 2u * (POL_N3 / 8) * 128u;
-        uint32_t ph_a = 0, ph_h = 0;
-        mbar_wait(bar_w, 0);
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            mbar_wait(bar_a, ph_a);
-            ph_a ^= 1u;
-            tc_fence_after();
-            if (lane == 0) {
+        if (lane == 0) {
+            uint32_t ph_h = 0, j = 0;
+            if (p.trace && blockIdx.x == 0) trace_role = p.trace + 2 * POLICY_TRACE_LEN;
+            mbar_wait(bar_w, 0);
+            for (long long tile = first_tile; tile < n_tiles; tile += stride, ++j) {
+                const uint32_t P = tmem + ((j & 1u) ? 256u : 0u), Q = tmem + ((j & 1u) ? 0u : 256u);
+                mark();                                        // M0: waiting for x(j) and MMA3(j-1)
+                mbar_wait(bar_a, j & 1u);
+                if (j > 0) mbar_wait(bar_d3, (j - 1u) & 1u);  // MMA3(j-1) has read h2(j-1) out of P(j)
+                tc_fence_after();
+                mark();                                        // M1: issuing MMA1
 #pragma unroll
                 for (uint32_t k = 0; k < POLICY_K1 / 16; ++k)
-                    tc_mma_ts(tmem, tmem + 256u + 8u * k, b_desc(sm + OFF_W1 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
-                tc_commit(bar_d);
-            }
-            __syncwarp();
-            // layers 2 and 3 run behind the epilogue that produces their operand: two MMAs (K = 32) per announced chunk
+                    tc_mma_ts(P, Q + 192u + 8u * k, b_desc(sm + OFF_W1 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
+                tc_commit(bar_d1);
+                // layers 2 and 3 run behind the epilogue that produces their operand: two MMAs (K = 32) per announced chunk
 #pragma unroll 1
-            for (uint32_t c = 0; c < 8; ++c) {
-                mbar_wait(bar_h + 8 * c, ph_h);
-                tc_fence_after();
-                if (lane == 0) {
+                for (uint32_t i = 0; i < 8; ++i) {
+                    const uint32_t c = POL_HGROUPS == 1 ? i : (i >> 1) + 4u * (i & 1u);
+                    mbar_wait(bar_h + 8 * c, ph_h);
+                    if (i == 0 && j > 0) mbar_wait(bar_c, (j - 1u) & 1u);  // the logits of tile j-1 have left Q(j)[64, 96)
+                    tc_fence_after();
 #pragma unroll
                     for (uint32_t k = 2 * c; k < 2 * c + 2; ++k)
-                        tc_mma_ts(tmem + 256u, tmem + hidden_col(c) + 8u * (k & 1u),
-                                  b_desc(sm + OFF_W2 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
-                    if (c == 7) tc_commit(bar_d);
+                        tc_mma_ts(Q, P + hidden_col(c) + 8u * (k & 1u), b_desc(sm + OFF_W2 + k * KSTEP_H, POLICY_HIDDEN), I256, i + (k & 1u));
+                    if (i == 7) tc_commit(bar_d2);
+                    mark();                                    // M2..M9: MMA2 chunk issued
                 }
-                __syncwarp();
-            }
-            ph_h ^= 1u;
+                ph_h ^= 1u;
 #pragma unroll 1
-            for (uint32_t c = 0; c < 8; ++c) {
-                mbar_wait(bar_h + 8 * c, ph_h);
-                tc_fence_after();
-                if (lane == 0) {
+                for (uint32_t i = 0; i < 8; ++i) {
+                    const uint32_t c = POL_HGROUPS == 1 ? i : (i >> 1) + 4u * (i & 1u);
+                    mbar_wait(bar_h + 8 * c, ph_h);
+                    tc_fence_after();
 #pragma unroll
                     for (uint32_t k = 2 * c; k < 2 * c + 2; ++k)
-                        tc_mma_ts(tmem + POL_D3_COL, tmem + 256u + hidden_col(c) + 8u * (k & 1u),
-                                  b_desc(sm + OFF_W3 + k * KSTEP_3, POL_N3), I32, k);
-                    if (c == 7) tc_commit(bar_d);
+                        tc_mma_ts(P + POL_D3_COL, Q + hidden_col(c) + 8u * (k & 1u), b_desc(sm + OFF_W3 + k * KSTEP_3, POL_N3), I32, i + (k & 1u));
+                    if (i == 7) tc_commit(bar_d3);
+                    mark();                                    // M10..M17: MMA3 chunk issued
                 }
-                __syncwarp();
+                ph_h ^= 1u;
             }
-            ph_h ^= 1u;
         }
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();

@@ -25,7 +25,9 @@ struct PolicyParams {
     float *logits;           // [B, 26] or null (unmasked logits)
     float *value;            // [B]: when set, the packed network is a value head and nothing else is written
     float *dbg1, *dbg2;      // [B, 256] pre-activations of the two hidden layers (tests), or null
+    long long *trace;        // [3][POLICY_TRACE_LEN] clock64() marks of CTA 0's three roles (measurement aid), or null
 };
+constexpr int POLICY_TRACE_LEN = 2048;
 
 cudaError_t launch_policy_pack(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
                                const float *b3, int D, int n_out, void *packed, cudaStream_t s);
