@@ -58,19 +58,30 @@ class RolloutStorage:
 
 
 @torch.no_grad()
-def collect(policy, env, storage, sample_seed=0):
-    """T lockstep steps of every env under `policy`; the env writes slices 1..T of the storage."""
+def collect(policy, env, storage, sample_seed=0, fused=None):
+    """T lockstep steps of every env under `policy`; the env writes slices 1..T of the storage.
+    With `fused` (a skyjo_rl_b200.policy.FusedPolicy of the same policy) the whole policy side of a step -- forward,
+    masked softmax, sample, log-probability, and the value branch -- runs in the library's tensor-core kernels on
+    the bound observation slice; otherwise in ATen."""
     st = storage
     st.prime(env)
     for t in range(st.T):
-        logits = policy({"observations": st.obs[t], "action_mask": st.mask[t]})
-        st.value[t].copy_(policy.value_function())
-        env.sample_actions(logits.contiguous(), st.mask[t], seed=sample_seed, actions=st.action[t], logp=st.logp[t])
+        if fused is not None:
+            # the env's bound outputs ARE slice t (slice T of the previous rollout, copied to slot 0, for t = 0)
+            fused.sample(sample_seed, actions=st.action[t], logp=st.logp[t])
+            fused.value(out=st.value[t])
+        else:
+            logits = policy({"observations": st.obs[t], "action_mask": st.mask[t]})
+            st.value[t].copy_(policy.value_function())
+            env.sample_actions(logits.contiguous(), st.mask[t], seed=sample_seed, actions=st.action[t], logp=st.logp[t])
         env.bind_outputs(observations=st.obs[t + 1], action_mask=st.mask[t + 1], agent_selection=st.agent[t + 1],
                          done_code=st.done[t], rewards=st.reward[t], final_scores=st._final)
         env.step(st.action[t])
-    policy({"observations": st.obs[st.T], "action_mask": st.mask[st.T]})
-    st.value[st.T].copy_(policy.value_function())
+    if fused is not None:
+        fused.value(out=st.value[st.T])
+    else:
+        policy({"observations": st.obs[st.T], "action_mask": st.mask[st.T]})
+        st.value[st.T].copy_(policy.value_function())
     return st
 
 
@@ -121,9 +132,15 @@ def gae_turn_based(value, agent, done, reward, gamma=0.99, lam=1.0):
 
 class PPOTrainer:
     def __init__(self, env, policy=None, rollout_len=64, lr=5e-5, gamma=0.99, lam=1.0, clip=0.3, vf_clip=10.0,
-                 vf_coef=1.0, ent_coef=0.0, epochs=4, minibatches=8, max_grad_norm=None, seed=0):
+                 vf_coef=1.0, ent_coef=0.0, epochs=4, minibatches=8, max_grad_norm=None, seed=0, fused=False):
         self.env = env
         self.policy = policy if policy is not None else ActionMaskPolicy(env.obs_len).to(env.device)
+        # fused=True: rollouts through the library's tcgen05 policy kernel (bf16 copies of the weights, repacked after
+        # every update; rows of at most 96 bytes); the PPO epochs themselves stay in fp32 autograd
+        self.fused = None
+        if fused:
+            from .policy import FusedPolicy
+            self.fused = FusedPolicy(self.policy, env, with_value=True)
         self.storage = RolloutStorage(env, rollout_len)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=lr)
         self.gamma, self.lam, self.clip, self.vf_clip = gamma, lam, clip, vf_clip
@@ -155,7 +172,9 @@ class PPOTrainer:
     def train_iteration(self):
         env, st = self.env, self.storage
         s0 = env.stats()
-        collect(self.policy, env, st, sample_seed=self.seed)
+        if self.fused is not None:
+            self.fused.repack()
+        collect(self.policy, env, st, sample_seed=self.seed, fused=self.fused)
         s1 = env.stats()
         adv, ret, valid = gae_turn_based(st.value, st.agent, st.done, st.reward, self.gamma, self.lam)
         T, B = st.T, st.B

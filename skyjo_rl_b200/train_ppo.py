@@ -33,6 +33,8 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--resume", default=None)
+    ap.add_argument("--fused", action="store_true",
+                    help="rollouts through the library's fused tensor-core policy kernel (csrc/skyjo_policy.cu)")
     ap.add_argument("--tf32", action="store_true",
                     help="let the learner's fp32 GEMMs (ATen) use TF32 tensor cores; the env path is integer and unaffected")
     a = ap.parse_args(argv)
@@ -50,7 +52,7 @@ def main(argv=None):
     env = BatchedSkyjoEnv(num_envs=a.envs, device=dev, seed=a.seed, first_global_env_id=rank * a.envs, **cfg)
     env.reset()
     tr = PPOTrainer(env, rollout_len=a.rollout_len, lr=a.lr, epochs=a.epochs, minibatches=a.minibatches,
-                    ent_coef=a.ent_coef, seed=a.seed + rank)
+                    ent_coef=a.ent_coef, seed=a.seed + rank, fused=a.fused)
     def rank_path(path):      # env state and generator are per rank (disjoint global env ids): one file per rank
         return path if world == 1 else f"{path}.rank{rank}"
 

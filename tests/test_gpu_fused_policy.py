@@ -116,3 +116,23 @@ def test_fused_policy_rejects_long_rows():
     env.reset()
     with pytest.raises(_lib.SkyjoError):
         FusedPolicy(ActionMaskPolicy(env.obs_len).to(env.device), env)
+
+
+def test_ppo_learns_with_fused_rollouts():
+    """The learner of config 4 with its rollouts through the fused kernel (bf16 sampling, fp32 PPO epochs; the
+    importance ratio absorbs the difference): self-play must still learn, as with ATen rollouts
+    (tests/test_gpu_policy.py::test_ppo_self_play_learns_to_lower_scores)."""
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    from skyjo_rl_b200.ppo import PPOTrainer
+    torch.manual_seed(0)
+    env = BatchedSkyjoEnv(num_envs=8192, num_players=3, seed=1, observe_other_player_indirect=True,
+                          reward_refunded=0.001)
+    env.reset()
+    tr = PPOTrainer(env, rollout_len=64, lr=3e-4, epochs=4, minibatches=8, ent_coef=0.01, fused=True)
+    hist = [tr.train_iteration() for _ in range(14)]
+    first = np.mean([h["mean_raw_score"] for h in hist[1:3]])
+    last = np.mean([h["mean_raw_score"] for h in hist[-2:]])
+    assert sum(h["illegal"] for h in hist) == 0
+    assert all(abs(h["kl"]) < 0.5 for h in hist)            # bf16 behaviour policy vs fp32 learner: a small, finite gap
+    assert first > 45 and last < 0.75 * first, (first, last)
+    env.check()
