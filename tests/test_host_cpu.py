@@ -386,3 +386,23 @@ def test_wide_host_expansions_equal_the_portable_ones(n, offset):
             assert (raw_o[:lo] == 99).all()
             if mode in (0, 3):   # the streaming versions write whole groups only: the bytes behind the last row stay untouched
                 assert (raw_o[lo + out.nbytes + 16:] == 99).all()
+
+
+def test_round2_entry_points_validate_their_arguments():
+    # the policy kernel's weight image, the side-stream all-reduce, the env-range knob, the host twins added in round 2:
+    # sizes and argument checks that need no device
+    L = _lib.load()
+    assert L.skyjo_policy_packed_bytes() == 96 * 256 * 2 + 256 * 256 * 2 + 256 * 32 * 2 + 2 * 256 * 4 + 32 * 4
+    assert L.skyjo_policy_trace_len() == 2048
+    one = C.c_void_p(16)
+    assert L.skyjo_policy_pack(67, 26, None, None, None, None, None, None, None, None) == 1
+    assert L.skyjo_policy_pack(97, 26, one, one, one, one, one, one, one, None) == 1 and b"96 bytes" in L.skyjo_last_error()
+    assert L.skyjo_policy_pack(67, 27, one, one, one, one, one, one, one, None) == 1
+    assert L.skyjo_policy_pack(67, 26, one, one, one, one, one, one, C.c_void_p(8), None) == 1      # misaligned image
+    assert L.skyjo_policy_sample(None, one, 0, one, None, None, None, None) == 1
+    assert L.skyjo_policy_value(None, one, one, None) == 1 and L.skyjo_policy_value(None, one, None, None) == 1
+    assert L.skyjo_policy_debug(None, one, None, None, None, None) == 1
+    assert L.skyjo_stats_allreduce_async(None, None, None, None) == 1 and L.skyjo_stats_allreduce_wait(None, None) == 1
+    assert L.skyjo_set_env_ranges(None, 2) == 1 and L.skyjo_host_wire_share(None) == -1
+    assert L.skyjo_set_host_wire(None, 2) == 1
+    assert L.skyjo_host_simd_level() in (0, 2, 3)
