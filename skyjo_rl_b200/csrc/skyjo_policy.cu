@@ -7,7 +7,7 @@
 //
 // The three matrix products are the only contractions near the hot path, and they run on the 5th-generation
 // tensor cores: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in tensor memory), M = 128 envs per
-// tile, issued by one thread.  Layout of one persistent CTA (one per SM, 160 threads):
+// tile, issued by one thread.  Layout of one persistent CTA (one per SM, 288 threads):
 //   * shared memory holds the three weight matrices for the whole launch (bf16, 192 KB, in the canonical K-major
 //     no-swizzle core-matrix layout the MMA descriptors address: 8 rows x 16 bytes per core matrix), the biases,
 //     and the obs / mask rows of the tile being started (1-D TMA bulk copies, one tile ahead);
@@ -155,6 +155,10 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
 // fp32 bits and keeping the high half (PRMT packs two), an int8 observation becomes a float through the 1.5 x 2^23
 // trick and is exact in its high half.  Floor: 512 tanh per env x 16 cycles / 32 lanes / 4 schedulers per SM
 // = 8192 cycles per 128-env tile = 58 us per 2^18 envs at 1.965 GHz, 2.6 times the kernel's tensor-core time.
+// Also measured and rejected: three of every four units as sign(a) (1 - u) / (1 + u), u = exp2(-2 log2(e) |a|)
+// (one ex2: 8 XU cycles) with 1 / (1 + u) as a degree-4 minimax polynomial on the FMA pipe (2.2e-4 accurate) --
+// XU time per chunk 320 instead of 512 cycles on paper, but the ten issue slots per unit of a lone warp per
+// scheduler take longer than the pipe they relieve: 114 us against 89.5 (119 with two H warps per scheduler).
 __device__ __forceinline__ float tanh_f32(float x) {
 #ifdef SKYJO_POLICY_EXP_NOTANH  // timing experiment only: what the kernel costs without its SFU work
     return x;
@@ -183,8 +187,8 @@ __host__ __device__ constexpr uint32_t hidden_col(uint32_t c) {
 // 128 rows have announced it on bar_h[c].
 __device__ __forceinline__ void hidden_epilogue(uint32_t region, int group, const float *s_bias, float *dbg_row,
                                                 uint32_t bar_h) {
-#pragma unroll 1
     constexpr int PER = 8 / POL_HGROUPS;
+#pragma unroll 1
     for (int c = PER * group; c < PER * group + PER; ++c) {
         uint32_t v[32];
         tc_ld32(region + 32 * c, v);
