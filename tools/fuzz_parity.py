@@ -9,6 +9,8 @@
                                                      # the C oracle: random injected decks (standard and dense), N = 1..12
 
     python tools/fuzz_parity.py gpu       SECONDS    # the same as hostsim, on the CUDA build (under gpurun)
+    python tools/fuzz_parity.py gpu-chunked SECONDS  # skyjo_step_random(n >= 2) on the CUDA build: env-range streams and
+                                                     # refill windows, every env against the oracle at chunk boundaries
     python tools/fuzz_parity.py reference-strategy SECONDS   # the live reference vs the oracle on strategy-played games
     python tools/fuzz_parity.py strategy  SECONDS    # host-compiled kernels vs the C oracle on games played by the
                                                      # hoarder / hunter / closer strategies (tests/test_strategy_games.py)
@@ -56,6 +58,33 @@ def fuzz_hostsim(seconds, gpu=False):
             print("MISMATCH", params, flush=True)
             traceback.print_exc()
     print(f"{'GPU' if gpu else 'hostsim'} vs oracle: {runs} runs ok, {bad} mismatches")
+    return bad
+
+
+def fuzz_chunked(seconds):
+    """The multi-stream / refill-window path of skyjo_step_random on the CUDA build (under gpurun): random player
+    counts, env-range counts, chunk lengths (the window length depends on N), reset modes -- every env against the
+    oracle at every chunk boundary, plus the exported state (tests/parity_util.chunked_rollout)."""
+    import parity_util as P
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    rng = np.random.default_rng(int(time.time()))
+    t_end, runs, bad, steps = time.time() + seconds, 0, 0, 0
+    while time.time() < t_end:
+        N, ind, mode = int(rng.integers(1, 13)), bool(rng.integers(2)), int(rng.choice([1, 2]))
+        B, ranges = int(rng.integers(1, 1500)), int(rng.integers(1, 9))
+        chunks = [int(rng.choice([2, 3, 7, 8, 9, 16, 31, 32, 33, 40, 64, 70])) for _ in range(int(rng.integers(4, 14)))]
+        params = dict(N=N, indirect=ind, mode=mode, B=B, ranges=ranges, chunks=chunks)
+        try:
+            s, _, _ = P.chunked_rollout(lambda **kw: BatchedSkyjoEnv(**kw), N, ind, float(rng.choice([1.0, 2.0, 3.3])), 1.0,
+                                        float(rng.choice([0.0, 0.01])), B, chunks, reset_mode=mode, ranges=ranges,
+                                        seed=int(rng.integers(1, 10 ** 6)), first_env=int(rng.integers(0, 10 ** 9)))
+            runs += 1
+            steps += s
+        except AssertionError:
+            bad += 1
+            print("MISMATCH", params, flush=True)
+            traceback.print_exc()
+    print(f"GPU chunked step_random vs oracle: {runs} runs ok ({steps} env-steps), {bad} mismatches")
     return bad
 
 
@@ -148,5 +177,6 @@ def fuzz_reference_strategy(seconds):
 if __name__ == "__main__":
     which, seconds = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
     fn = {"hostsim": fuzz_hostsim, "reference": fuzz_reference, "strategy": fuzz_strategy,
-          "gpu": lambda sec: fuzz_hostsim(sec, gpu=True), "reference-strategy": fuzz_reference_strategy}[which]
+          "gpu": lambda sec: fuzz_hostsim(sec, gpu=True), "gpu-chunked": fuzz_chunked,
+          "reference-strategy": fuzz_reference_strategy}[which]
     sys.exit(1 if fn(seconds) else 0)
