@@ -237,7 +237,8 @@ int skyjo_set_host_threads(SkyjoHandle *h, int n);
  * into obs_host by the copy engine (no CPU work); 1 = compact records of 12 + 6 R + ceil(R / 2) bytes for a row of
  * 19 + 12 R bytes, packed on the device and expanded on the host by the worker threads (1.7x fewer bytes on the
  * link, paid for in host memory traffic); 2 = mixed: the first k of 8 ranges compact, the rest raw, k tuned between
- * calls by measurement (perturb and observe on the call time, starting from k = 0).  Default: 2 where the CPU has the
+ * calls by measurement (perturb and observe on the call time, starting from k = 4 / 2 / 0 for 1 / 2-3 / >= 4 ranks
+ * on the host, LOCAL_WORLD_SIZE).  Default: 2 where the CPU has the
  * AVX-512 streaming expansions (skyjo_host_simd_level() == 2), else 0; env SKYJO_HOST_WIRE=raw|compact|mixed
  * selects at creation, SKYJO_HOST_MIX=k pins the share.  All modes fill the host buffers bit-identically. */
 int skyjo_set_host_wire(SkyjoHandle *h, int mode);
