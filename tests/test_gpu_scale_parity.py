@@ -111,3 +111,45 @@ def test_side_stream_stats_allreduce_snapshots_iteration_boundaries():
             assert got[-1].data_ptr() != got[-2].data_ptr()
     assert int(want[-1][16]) > int(want[0][16]) > 0
     env.check()
+
+
+@pytest.mark.parametrize("N,B,mode,T", [(4, 1 << 18, 1, 300), (4, 1 << 18, 2, 300), (3, 1 << 17, 1, 260)])
+def test_external_action_path_matches_oracle_on_sampled_envs_at_scale(N, B, mode, T):
+    """The path of BASELINE config 4 and of skyjo_step_host -- skyjo_step with actions from outside, one refill deal
+    per step -- at 2^18 envs: actions drawn on the device from the mask (as a policy would), 0.3 % of the sampled
+    envs given an illegal action per step; every step obs / mask / agent / done / float64 rewards of 384 sampled envs
+    against OracleBatch (SkyjoGame.act + TerminateIllegalWrapper semantics + the reset schedule)."""
+    from parity_util import OracleBatch, to_np
+    ids = sample_blocks(B, n_blocks=8, width=32, ranges=4)[:384]
+    seed, first = 77 + N, 10_000_000
+    env = _env(num_envs=B, num_players=N, score_penalty=2.0, mean_reward=1.0, reward_refunded=0.25, seed=seed,
+               auto_reset=mode, first_global_env_id=first)
+    env.reset()
+    ref = OracleBatch(N, False, 2.0, 1.0, 0.25, seed, len(ids), first, mode, 0, env_ids=[first + int(i) for i in ids])
+    tid = torch.as_tensor(ids, device=env.device)
+    rng = np.random.default_rng(5)
+    g = torch.Generator(device=env.device)
+    g.manual_seed(3)
+    ended = illegal = 0
+    for t in range(T):
+        obs, mask, agent = ref.publish()
+        np.testing.assert_array_equal(to_np(env.observations[tid]), obs, err_msg=f"obs at step {t}")
+        np.testing.assert_array_equal(to_np(env.action_mask[tid]), mask, err_msg=f"mask at step {t}")
+        np.testing.assert_array_equal(to_np(env.agent_selection[tid]), agent, err_msg=f"agent at step {t}")
+        a = torch.multinomial(env.action_mask.float(), 1, generator=g).squeeze(1).to(torch.uint8)
+        bad = np.flatnonzero(rng.random(len(ids)) < 0.003)
+        for i in bad:                                  # an action of the other phase, or out of range
+            a[int(ids[i])] = int(rng.choice(np.flatnonzero(mask[i] == 0))) if rng.random() < 0.7 else int(rng.integers(26, 200))
+        act = to_np(a[tid]).astype(np.int64)
+        done, reward, score = ref.step(act, mask, agent)
+        env.step(a)
+        np.testing.assert_array_equal(to_np(env.done_code[tid]), done, err_msg=f"done at step {t}")
+        assert to_np(env.rewards[tid]).tobytes() == reward.tobytes(), f"rewards at step {t}"
+        scored = (done == 1) & ~np.isnan(score[:, 0])
+        assert to_np(env.final_scores[tid])[scored].tobytes() == score[scored].tobytes(), f"scores at step {t}"
+        ended += int((done == 1).sum())
+        illegal += int((done == 2).sum())
+    env.check()
+    assert ended > len(ids) // 2 and illegal > 0, (ended, illegal)
+    st = env.stats()
+    assert st["illegal"] >= illegal and st["episodes"] > B // 2
