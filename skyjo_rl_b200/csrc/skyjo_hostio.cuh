@@ -13,7 +13,8 @@
 //     by the previous call are re-zeroed first.  If more envs finish than the buffer holds
 //     (mass illegal actions) the call falls back to copying the dense reward tensor.
 //   * observations (D bytes per env) are copied as they are, straight into the caller's buffer (wire mode 0).
-//     Wire mode 1 (opt-in) sends COMPACT RECORDS instead: every byte of an observation row (skyjo.py:180-190) is
+//     Wire mode 1 sends COMPACT RECORDS instead (mode 2, the default where the CPU has AVX-512, for a measured share of
+//     the env ranges -- skyjo_capi.cu skyjo_step_host): every byte of an observation row (skyjo.py:180-190) is
 //     one of a few small symbols -- a card is -2..12, 15 (hidden) or -14 (removed column), a histogram bin is a
 //     count <= 15 (the value-0 bin, which receives three zeros per column removal, up to a byte), the discard
 //     top is -3..12 -- so a row of D = 19 + 12 R bytes packs into 12 + 6 R + ceil(R / 2) bytes
@@ -21,10 +22,10 @@
 //     packs the published rows on the device, the host expands them into the caller's int8[B, D] buffer with
 //     16-byte shuffles (pshufb as the nibble -> card value table).  A row that holds anything else (it cannot,
 //     by the state layout: 4-bit bins) raises a flag and the call falls back to the dense copy.
-//     Measured (B200 box, 16 host threads, N = 4, 2^20 envs): 42 instead of 71 B per env on the link, but the
-//     expansion writes 95 B per env through the CPU (plus the read-for-ownership of every line) where the copy
-//     engine wrote them for free: 5.4e8 env-steps/s against 7.3e8 in mode 0.  It pays only when the link is
-//     slower than the host's memory system.
+//     (AVX-512 hosts: byte gathers and streaming stores, skyjo_hostsimd.cpp.)  Measured (B200 boxes, N = 4, 2^20
+//     envs): 42 instead of 71 B per env on the link, but the expansion writes 95 B per env through the CPUs where the
+//     copy engine wrote them for free, and the two share the host's memory system: all ranges compact 5.8-7.0e8
+//     env-steps/s, all raw 7.2e8, four of eight compact 7.7-8.0e8 at 1 GPU; at 8 GPUs raw wins.
 // The batch is processed in up to HOSTIO_MAX_CHUNKS env ranges (step kernel, pack kernel and copies
 // per range), so that the link is already busy with range c while the GPU steps range c + 1.
 // N = 4, direct observations: 67 + 4 = 71 B per env-step (38 + 4 = 42 B in wire mode 1) instead of 127 B.
