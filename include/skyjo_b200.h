@@ -224,7 +224,10 @@ int skyjo_step_random_profile(SkyjoHandle *h, int n_steps, void *stream, double 
  * env and are expanded on the host by a few worker threads; reward rows cross only for envs
  * whose episode ended in this step, the other rows are zero-filled on the host; observation
  * rows are copied as they are (or as compact records, skyjo_set_host_wire).  Use pinned host
- * buffers for full link speed, and the same reward buffer on consecutive calls. */
+ * buffers for full link speed, and the same reward buffer on consecutive calls.
+ * Batches of at most 256 envs take a latency path instead: the actions are read through a host-mapped pointer,
+ * one block writes all outputs into host-mapped pinned memory, the host polls a sequence word and copies them
+ * into the caller's buffers (any host memory), and the refill deal is launched only when an episode ended. */
 int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host,
                     int8_t *mask_host, int8_t *agent_host, uint8_t *done_host,
                     double *reward_host, void *stream);

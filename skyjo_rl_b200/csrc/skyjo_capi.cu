@@ -115,6 +115,8 @@ struct SkyjoHandle {
     unsigned int *counter_dev, *counter_host;   // [2]: finished envs of the call, "row not encodable" flag
     uint8_t *rec_dev, *rec_host;            // compact observation records, [B][obs_record_bytes(D)]
     cudaEvent_t ev_rec_done[HOSTIO_MAX_CHUNKS];
+    uint8_t *small_host, *small_dev;        // host-mapped staging of the small-batch path (B <= SMALL_HOST_MAX)
+    unsigned int small_seq;
     int wire_mode;                          // 0 raw rows, 1 compact records, 2 mixed (adaptive share of the env ranges)
     // mixed mode: mix_k of 8 env ranges travel as compact records.  The share is tuned by measurement: the mean
     // call time of every window of 6 calls is filed under its k; the next window runs at the untried neighbour of
@@ -295,6 +297,8 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     for (double &v : h->mix_t) v = -1.0;
     h->last_d2h_bytes = 0;
     h->rec_dev = h->rec_host = nullptr;
+    h->small_host = h->small_dev = nullptr;
+    h->small_seq = 0;
     h->last_reward_host = nullptr;
     h->trace_calls = 0;
     for (double &v : h->trace_us) v = 0.0;
@@ -318,6 +322,12 @@ static void hostio_release(SkyjoHandle *h) {
     }
     delete h->pool;
     h->pool = nullptr;
+    if (h->small_host) {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        cudaFreeHost(h->small_host);
+        h->small_host = h->small_dev = nullptr;
+    }
     if (!h->hostio_ready) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->copy_stream);
@@ -810,11 +820,65 @@ static int hostio_init(SkyjoHandle *h) {
     return SKYJO_OK;
 }
 
+// skyjo_step_host for B <= SMALL_HOST_MAX envs: latency path (skyjo_hostio.cuh, publish_small_kernel)
+static int step_host_small(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host, int8_t *mask_host,
+                           int8_t *agent_host, uint8_t *done_host, double *reward_host, cudaStream_t s) {
+    const size_t B = (size_t)h->B, N = (size_t)h->cfg.num_players, D = (size_t)h->obs_len;
+    const SmallLayout L = small_layout(B, D, N);
+    if (!h->small_host) {
+        CU(cudaHostAlloc(&h->small_host, L.total, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer(&h->small_dev, h->small_host, 0));
+        memset(h->small_host, 0, L.total);
+    }
+    int rc = quiesce(h, s);
+    if (rc) return rc;
+    memcpy(h->small_host + L.act, actions_host, B);
+    StepParams p = make_params(h);
+    p.actions = h->small_dev + L.act;
+    p.action_dtype = SKYJO_ACT_U8;
+    CU(kStep[h->cfg.num_players - 1](p, h->cfg.observe_other_player_indirect != 0, false, s));
+    const unsigned int seq = ++h->small_seq ? h->small_seq : ++h->small_seq;  // never 0
+    publish_small_kernel<<<1, 256, 0, s>>>((const int8_t *)h->outs.obs_dev, (const int8_t *)h->outs.action_mask_dev,
+                                           (const int8_t *)h->outs.agent_dev, (const uint8_t *)h->outs.done_dev,
+                                           (const double *)h->outs.reward_dev, h->B, (int)D, (int)N, h->small_dev, seq);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    h->t += 1;
+    // poll the sequence word; past ~2 ms something is wrong: let the stream report it
+    volatile unsigned int *flag = reinterpret_cast<volatile unsigned int *>(h->small_host);
+    const auto t0 = std::chrono::steady_clock::now();
+    while (flag[0] != seq) {
+#if defined(__x86_64__)
+        _mm_pause();
+#endif
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) {
+            CU(cudaStreamSynchronize(s));
+            if (flag[0] != seq) return fail(SKYJO_E_STATE, "skyjo_step_host: the outputs never arrived in host memory");
+        }
+    }
+    if (obs_host) memcpy(obs_host, h->small_host + L.obs, B * D);
+    if (mask_host) memcpy(mask_host, h->small_host + L.mask, B * 26);
+    if (agent_host) memcpy(agent_host, h->small_host + L.agent, B);
+    if (done_host) memcpy(done_host, h->small_host + L.done, B);
+    if (reward_host) memcpy(reward_host, h->small_host + L.reward, B * N * 8);
+    h->last_reward_host = nullptr;
+    h->last_d2h_bytes = (long long)(L.total - L.obs);
+    // the refill deal only when an episode ended (external actions may end one at any step)
+    if (flag[1] != 0u) {
+        h->steps_since_deal = 1;
+        return close_window(h, s, false);
+    }
+    h->steps_since_deal = 0;
+    return SKYJO_OK;
+}
+
 int skyjo_step_host(SkyjoHandle *h, const uint8_t *actions_host, int8_t *obs_host, int8_t *mask_host,
                     int8_t *agent_host, uint8_t *done_host, double *reward_host, void *stream) {
     if (!h || !actions_host) return fail(SKYJO_E_INVALID, "null argument");
     if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
     CU(cudaSetDevice(h->device));
+    if (h->B <= SMALL_HOST_MAX && !getenv("SKYJO_HOST_NO_SMALL"))
+        return step_host_small(h, actions_host, obs_host, mask_host, agent_host, done_host, reward_host, (cudaStream_t)stream);
     int rc = hostio_init(h);
     if (rc) return rc;
     if (!h->pool) h->pool = new (std::nothrow) HostPool(h->host_threads > 0 ? h->host_threads : default_host_threads());

@@ -86,6 +86,57 @@ __global__ void __launch_bounds__(256) pack_host_kernel(const U128 *planes, long
 }
 
 
+// ---- small batches: one block publishes everything into host-mapped memory ---------------------------
+// For a handful of envs (the single-env PettingZoo view, skyjo_rl_b200/aec.py) a call is latency, not bandwidth:
+// the step kernel reads the actions through a host-mapped pointer and this one-block kernel writes the
+// published outputs straight into host-mapped pinned memory, followed by a sequence number the host polls --
+// no copy-engine transfers, no event, and the refill deal is launched only when an env finished.
+// Staging layout (bytes): [0, 16) seq + finished count, then actions B (padded to 16), obs B x D, mask B x 26,
+// agent B, done B (each padded to 16), reward B x N doubles.
+constexpr long long SMALL_HOST_MAX = 256;
+__host__ __device__ inline size_t small_pad16(size_t n) { return (n + 15) & ~(size_t)15; }
+struct SmallLayout {
+    size_t act, obs, mask, agent, done, reward, total;
+};
+__host__ __device__ inline SmallLayout small_layout(size_t B, size_t D, size_t N) {
+    SmallLayout L;
+    L.act = 16;
+    L.obs = L.act + small_pad16(B);
+    L.mask = L.obs + small_pad16(B * D);
+    L.agent = L.mask + small_pad16(B * 26);
+    L.done = L.agent + small_pad16(B);
+    L.reward = L.done + small_pad16(B);
+    L.total = L.reward + B * N * 8;
+    return L;
+}
+__global__ void __launch_bounds__(256) publish_small_kernel(const int8_t *obs, const int8_t *mask, const int8_t *agent,
+                                                            const uint8_t *done, const double *reward, long long B,
+                                                            int D, int N, uint8_t *stage, unsigned int seq) {
+    const SmallLayout L = small_layout((size_t)B, (size_t)D, (size_t)N);
+    const int t = threadIdx.x;
+    __shared__ unsigned int s_fin;
+    if (t == 0) s_fin = 0;
+    __syncthreads();
+    for (long long i = t; i < B * D; i += 256) stage[L.obs + i] = (uint8_t)obs[i];
+    for (long long i = t; i < B * 26; i += 256) stage[L.mask + i] = (uint8_t)mask[i];
+    unsigned int fin = 0;
+    for (long long i = t; i < B; i += 256) {
+        stage[L.agent + i] = (uint8_t)agent[i];
+        stage[L.done + i] = done[i];
+        fin += done[i] != 0;
+    }
+    double *rw = reinterpret_cast<double *>(stage + L.reward);
+    for (long long i = t; i < B * N; i += 256) rw[i] = reward[i];
+    if (fin) atomicAdd(&s_fin, fin);
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) {
+        reinterpret_cast<volatile unsigned int *>(stage)[1] = s_fin;
+        __threadfence_system();
+        reinterpret_cast<volatile unsigned int *>(stage)[0] = seq;  // last: the host polls this word
+    }
+}
+
 // ---- compact observation records ------------------------------------------------------------------
 // Row layout (skyjo.py:180-190): [0] min open sum, [1] min hidden count, [2..16] 15-bin histogram (bin k = value
 // k - 2), [17] discard top, [18] hand card, [19 + 12 r + i] slot i of card row r (R = N rows, or the own row).
