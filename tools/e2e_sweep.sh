@@ -1,6 +1,9 @@
 #!/bin/bash
 # e2e (skyjo_step_host) sweep over wire mode / host threads / env ranges on a B200 box; outputs in gpurun_out/.
-# usage: bash tools/e2e_sweep.sh <tag> [players] [ngpus]
+# usage: bash tools/e2e_sweep.sh <tag> [players] [ngpus] [final|multi|nt|threads]
+#   (default) one run per wire mode / fixed share;  final: measured share vs raw, twice;  multi: the same set under
+#   torchrun at <ngpus>;  nt: streaming vs plain stores A/B (SKYJO_HOST_NT_MASK / SKYJO_HOST_NT are experiment knobs of
+#   csrc/skyjo_hostsimd.cpp);  threads: worker count, spin and pinning knobs.
 T=${1:-e2e}
 N=${2:-4}
 G=${3:-1}
@@ -52,9 +55,9 @@ exit 0
 fi
 if [ "$4" = "nt" ]; then
 for rep in 1 2; do
-run raw_t4_nt_$rep SKYJO_HOST_WIRE=raw SKYJO_HOST_THREADS=4
-run raw_t4_plain_$rep SKYJO_HOST_WIRE=raw SKYJO_HOST_THREADS=4 SKYJO_HOST_NT=0
-run raw_t2_plain_$rep SKYJO_HOST_WIRE=raw SKYJO_HOST_THREADS=2 SKYJO_HOST_NT=0
+run raw_t4_nt_$rep SKYJO_HOST_WIRE=raw SKYJO_HOST_THREADS=4 SKYJO_HOST_NT_MASK=1
+run raw_t4_plain_$rep SKYJO_HOST_WIRE=raw SKYJO_HOST_THREADS=4
+run raw_t2_plain_$rep SKYJO_HOST_WIRE=raw SKYJO_HOST_THREADS=2
 run mix5_t8_nt_$rep SKYJO_HOST_MIX=5 SKYJO_HOST_THREADS=8
 run mix5_t8_plain_$rep SKYJO_HOST_MIX=5 SKYJO_HOST_THREADS=8 SKYJO_HOST_NT=0
 run mix6_t8_nt_$rep SKYJO_HOST_MIX=6 SKYJO_HOST_THREADS=8
