@@ -425,18 +425,20 @@ __global__ void __launch_bounds__(POL_THREADS, 1) policy_kernel(const __grid_con
         constexpr uint32_t KSTEP_3 = 2u * (POL_N3 / 8) * 128u;
         if (lane == 0) {
             uint32_t ph_h = 0, j = 0;
+            const uint32_t k1_steps = (uint32_t)(D + 15) / 16u;  // 5 of 6 for the 67-byte rows of four players
             if (p.trace && blockIdx.x == 0) trace_role = p.trace + 2 * POLICY_TRACE_LEN;
             mbar_wait(bar_w, 0);
             for (long long tile = first_tile; tile < n_tiles; tile += stride, ++j) {
                 const uint32_t P = tmem + ((j & 1u) ? 256u : 0u), Q = tmem + ((j & 1u) ? 0u : 256u);
-                mark();                                        // M0: waiting for x(j) and MMA3(j-1)
+                mark();                                        // M0: waiting for x(j)
+                // No wait for MMA3(j-1), which reads h2(j-1) out of P(j): tcgen05.mma executes in issue order, and
+                // the raw D2(j-1) columns were consumed by team H before it announced the chunks MMA3(j-1) ran on.
                 mbar_wait(bar_a, j & 1u);
-                if (j > 0) mbar_wait(bar_d3, (j - 1u) & 1u);  // MMA3(j-1) has read h2(j-1) out of P(j)
                 tc_fence_after();
                 mark();                                        // M1: issuing MMA1
 #pragma unroll
-                for (uint32_t k = 0; k < POLICY_K1 / 16; ++k)
-                    tc_mma_ts(P, Q + 192u + 8u * k, b_desc(sm + OFF_W1 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
+                for (uint32_t k = 0; k < POLICY_K1 / 16; ++k)  // K-steps beyond the row length multiply zeros: skipped
+                    if (k < k1_steps) tc_mma_ts(P, Q + 192u + 8u * k, b_desc(sm + OFF_W1 + k * KSTEP_H, POLICY_HIDDEN), I256, k);
                 tc_commit(bar_d1);
                 // layers 2 and 3 run behind the epilogue that produces their operand: two MMAs (K = 32) per announced chunk
 #pragma unroll 1
