@@ -203,6 +203,73 @@ SKYJO_HD void store_env(U128 *planes, long long Bpad, long long e, const Env<N> 
             st128(planes + (long long)(1 + q) * Bpad + e, s.row[q].w0, s.row[q].w1, s.row[q].w2, s.row[q].w3);
 }
 
+// End-of-game scoring of one env by its own thread (skyjo.py:477-498, skyjo_env.py:293-312): raw scores, the
+// finisher's penalty, float64 rewards in numpy's summation order; writes reward / final_score rows and the
+// statistics fields of `oc`.  About one lane in 66 reaches it in a draw slot at N = 4, i.e. 39 % of the warps run
+// it with one or two active lanes.  SKYJO_SCORE_OUTLINE = 1 keeps it out of line on the device (a call instead of
+// 350 inlined instructions between the draw and the place transition); measured in DESIGN.md section 8.
+#ifndef SKYJO_SCORE_OUTLINE
+#define SKYJO_SCORE_OUTLINE 0
+#endif
+#if defined(__CUDACC__) && SKYJO_SCORE_OUTLINE
+#define SKYJO_SCORE_FN __host__ __device__ __noinline__
+#else
+#define SKYJO_SCORE_FN SKYJO_HD
+#endif
+#if defined(__CUDACC__) && SKYJO_SCORE_OUTLINE == 2  // by value: the caller's state stays in registers
+#define SKYJO_SCORE_ENV(N) const Env<N> s
+#else
+#define SKYJO_SCORE_ENV(N) const Env<N> &s
+#endif
+template <int N>
+SKYJO_SCORE_FN void score_game(const StepParams &p, long long e, SKYJO_SCORE_ENV(N), int cur, Outcome &oc) {
+    int raw[N];
+    int mn = 1 << 30, refunds = 0, raw_sum = 0;
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const Row &r = s.row[q];
+        uint32_t v[3];
+        row_cards(r, v);  // hidden cards count at their true value (skyjo.py:488-493)
+        raw[q] = score12(v);
+        mn = raw[q] < mn ? raw[q] : mn;
+        raw_sum += raw[q];
+        refunds += (int)sk_popc(row_flags(r));
+    }
+    int fin_raw = raw[0];
+#pragma unroll
+    for (int q = 1; q < N; ++q)
+        if (q == cur) fin_raw = raw[q];
+    const bool penalised = mn != fin_raw;  // skyjo.py:496
+    double score[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        score[q] = (double)raw[q];
+        if (penalised && q == cur) score[q] = sk_dmul(score[q], p.score_penalty);
+    }
+    // skyjo_env.py:307-311
+    const double mean = sk_ddiv(np_sum<N>(score), (double)N);
+    int winner = 0;
+    double best = score[0];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        double r = sk_dadd(sk_dadd(-score[q], mean), p.mean_reward);
+        if (p.reward_refunded != 0.0)
+            r = sk_dadd(r, sk_dmul((double)sk_popc(row_flags(s.row[q])), p.reward_refunded));
+        p.reward[e * N + q] = r;
+        p.final_score[e * N + q] = score[q];
+        if (score[q] < best) {
+            best = score[q];
+            winner = q;
+        }
+    }
+    oc.raw_sum = raw_sum;
+    oc.winner_raw = mn;
+    oc.fin_raw = fin_raw;
+    oc.penalised = penalised ? 1 : 0;
+    oc.refunds = refunds;
+    oc.winner = winner;
+}
+
 // One env-step for env e: SkyjoGame.act + rewards + (on episode end) auto-reset install.
 // `s` holds the loaded state and is updated in place; the caller stores it back.  With POLICY
 // the action is the uniform legal choice selected by `policy_rnd` = policy_random(seed, env, t).
@@ -282,51 +349,7 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
                     oc.refunds = as->refunds;
                     oc.winner = as->winner;
                 } else {
-                    int raw[N];
-                    int mn = 1 << 30, refunds = 0, raw_sum = 0;
-#pragma unroll
-                    for (int q = 0; q < N; ++q) {
-                        const Row &r = s.row[q];
-                        uint32_t v[3];
-                        row_cards(r, v);  // hidden cards count at their true value (skyjo.py:488-493)
-                        raw[q] = score12(v);
-                        mn = raw[q] < mn ? raw[q] : mn;
-                        raw_sum += raw[q];
-                        refunds += (int)sk_popc(row_flags(r));
-                    }
-                    int fin_raw = raw[0];
-#pragma unroll
-                    for (int q = 1; q < N; ++q)
-                        if (q == cur) fin_raw = raw[q];
-                    const bool penalised = mn != fin_raw;  // skyjo.py:496
-                    double score[N];
-#pragma unroll
-                    for (int q = 0; q < N; ++q) {
-                        score[q] = (double)raw[q];
-                        if (penalised && q == cur) score[q] = sk_dmul(score[q], p.score_penalty);
-                    }
-                    // skyjo_env.py:307-311
-                    const double mean = sk_ddiv(np_sum<N>(score), (double)N);
-                    int winner = 0;
-                    double best = score[0];
-#pragma unroll
-                    for (int q = 0; q < N; ++q) {
-                        double r = sk_dadd(sk_dadd(-score[q], mean), p.mean_reward);
-                        if (p.reward_refunded != 0.0)
-                            r = sk_dadd(r, sk_dmul((double)sk_popc(row_flags(s.row[q])), p.reward_refunded));
-                        p.reward[e * N + q] = r;
-                        p.final_score[e * N + q] = score[q];
-                        if (score[q] < best) {
-                            best = score[q];
-                            winner = q;
-                        }
-                    }
-                    oc.raw_sum = raw_sum;
-                    oc.winner_raw = mn;
-                    oc.fin_raw = fin_raw;
-                    oc.penalised = penalised ? 1 : 0;
-                    oc.refunds = refunds;
-                    oc.winner = winner;
+                    score_game<N>(p, e, s, cur, oc);
                 }
                 oc.starter0 = (((hdr >> HDR_STARTER_SH) & 0xF) == 0) ? 1 : 0;
             } else {
