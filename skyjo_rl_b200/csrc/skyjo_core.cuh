@@ -275,7 +275,11 @@ SKYJO_SCORE_FN void score_game(const StepParams &p, long long e, SKYJO_SCORE_ENV
 // the action is the uniform legal choice selected by `policy_rnd` = policy_random(seed, env, t).
 // With ASSIST the caller guarantees `as` carries the results of every rare event this step runs
 // into (a missing one raises ERR_ASSIST); without it (host build, tests/hostsim) the scalar code runs.
-template <int N, bool IND, bool POLICY, bool ASSIST = false>
+// With DEFER (device only, N below the assist threshold) a game that ends in the phase-locked reset mode is NOT
+// scored here: oc.scored = 2 asks the caller to score it with the whole warp right after this call
+// (skyjo_step.cuh warp_score_deferred) -- the rows stay in `s` because that mode installs the next episode one
+// slot later.  The other reset modes replace the rows below and keep the scalar scoring.
+template <int N, bool IND, bool POLICY, bool ASSIST = false, bool DEFER = false>
 SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int action, uint32_t policy_rnd = 0u,
                           const Assist *as = nullptr) {
     Outcome oc;
@@ -348,6 +352,8 @@ SKYJO_HD Outcome env_step(const StepParams &p, long long e, Env<N> &s, int actio
                     oc.penalised = as->penalised;
                     oc.refunds = as->refunds;
                     oc.winner = as->winner;
+                } else if (DEFER && p.auto_reset == 2) {
+                    oc.scored = 2;
                 } else {
                     score_game<N>(p, e, s, cur, oc);
                 }

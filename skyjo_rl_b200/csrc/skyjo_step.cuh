@@ -137,6 +137,11 @@ __device__ __forceinline__ bool install_next_step(int auto_reset, uint64_t hdr, 
     return auto_reset && next_hidden == 0u && !(hdr & (HDR_PHASE | HDR_TERMINATED));
 }
 
+// 1: below the assist threshold, games that end in the phase-locked mode are scored by the warp after env_step
+// (warp_score_deferred).  Bit-exact (the GPU parity suites pass with it) but measured slower, see there: off.
+#ifndef SKYJO_DEFER_SCORING
+#define SKYJO_DEFER_SCORING 0
+#endif
 // ---- warp assist for the rare, long events ---------------------------------------------------------
 // End-of-game scoring (skyjo.py:477-498 + skyjo_env.py:293-312: N rows of 12 cards, float64 rewards)
 // and the discard-only histogram of an in-game reshuffle in direct mode (12 N table slots) hit about
@@ -147,6 +152,96 @@ __device__ __forceinline__ bool install_next_step(int auto_reset, uint64_t hdr, 
 // row per lane, and reductions bring the results back to the owning lane, which hands them to
 // env_step<.., ASSIST = true>.  The arithmetic (order of the float64 sums included) is that of the
 // scalar code in skyjo_core.cuh, which the host build and tests/hostsim keep using.
+// End-of-game scoring by the warp (skyjo.py:477-498 + skyjo_env.py:293-312), called by all 32 lanes: lane q < N
+// (`act`) holds row q of the env whose global index is eL, `fin` is its finisher; rewards and final scores are
+// stored by the N lanes, the reduced statistics land in `as` of the lane with `owner`.  Same arithmetic, float64
+// summation order included, as score_game (skyjo_core.cuh).
+template <int N>
+__device__ __forceinline__ void warp_score_row(const StepParams &p, const Row &mine, bool act, int fin, long long eL,
+                                               int lane, bool owner, Assist &as) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    uint32_t v[3];
+    row_cards(mine, v);  // hidden cards count at their true value (skyjo.py:488-493)
+    const int raw = score12(v);
+    const int ref = (int)sk_popc(row_flags(mine));
+    const int mn = __reduce_min_sync(FULL, act ? raw : 0x7FFFFFFF);
+    const int raw_sum = __reduce_add_sync(FULL, act ? raw : 0);
+    const int refunds = __reduce_add_sync(FULL, act ? ref : 0);
+    const int fin_raw = __shfl_sync(FULL, raw, fin);
+    const bool penalised = mn != fin_raw;  // skyjo.py:496
+    double sc = (double)raw;
+    if (penalised && lane == fin) sc = sk_dmul(sc, p.score_penalty);
+    double a[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) a[q] = __shfl_sync(FULL, sc, q);
+    const double mean = sk_ddiv(np_sum<N>(a), (double)N);  // skyjo_env.py:307-311
+    int winner = 0;
+    double best = a[0];
+#pragma unroll
+    for (int q = 1; q < N; ++q)
+        if (a[q] < best) {
+            best = a[q];
+            winner = q;
+        }
+    if (act) {
+        double r = sk_dadd(sk_dadd(-sc, mean), p.mean_reward);
+        if (p.reward_refunded != 0.0) r = sk_dadd(r, sk_dmul((double)ref, p.reward_refunded));
+        p.reward[eL * N + lane] = r;
+        p.final_score[eL * N + lane] = sc;
+    }
+    if (owner) {
+        as.scored = 1;
+        as.raw_sum = raw_sum;
+        as.winner_raw = mn;
+        as.fin_raw = fin_raw;
+        as.penalised = penalised ? 1 : 0;
+        as.refunds = refunds;
+        as.winner = winner;
+    }
+}
+
+// Deferred scoring below the assist threshold (phase-locked reset mode only): env_step<.., DEFER> left
+// oc.scored == 2 on the lanes whose game just ended and their rows in `s`.  One such lane after the other hands
+// its N rows through `scratch` (the warp's staging tile, not yet in use) to lanes 0..N-1, which score one row each
+// -- about 120 warp-instructions per ended game instead of 350 executed by a single active lane (39 % of the
+// warps of a draw slot hold such a lane at N = 4).  No test runs before env_step and nothing stays live across it.
+// Measured on B200 (2^20 envs, next-step reset): step kernel 44.13 against 43.91 us at N = 4, 38.84 against 38.30
+// at N = 2; rollout kernel 31.46 against 30.15 us per step (its spills grow from 24 to 80 bytes).  The issue slots
+// of the one-lane block are slots the SM had free (issue 66 % busy): removing them buys nothing, the ballot and the
+// second warp-wide phase cost a little.  Kept behind SKYJO_DEFER_SCORING, off.
+template <int N>
+__device__ __forceinline__ void warp_score_deferred(const StepParams &p, const Env<N> &s, long long e, int lane,
+                                                    uint8_t *scratch, Outcome &oc) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    unsigned need = __ballot_sync(FULL, oc.scored == 2);
+    uint4 *sc4 = reinterpret_cast<uint4 *>(scratch);
+    const int cur = (int)(s.hdr >> HDR_CUR_SH) & 0xF;  // the finisher: a game-ending draw does not advance the turn
+    while (need) {  // warp-uniform
+        const int L = __ffs(need) - 1;
+        need &= need - 1u;
+        if (lane == L) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) sc4[k] = make_uint4(s.row[k].w0, s.row[k].w1, s.row[k].w2, s.row[k].w3);
+        }
+        __syncwarp();
+        const bool act = lane < N;
+        const uint4 t = sc4[act ? lane : 0];
+        __syncwarp();
+        const Row mine = {t.x, t.y, t.z, t.w};
+        Assist as;
+        warp_score_row<N>(p, mine, act, __shfl_sync(FULL, cur, L), e - lane + L, lane, lane == L, as);
+        if (lane == L) {
+            oc.scored = 1;
+            oc.raw_sum = as.raw_sum;
+            oc.winner_raw = as.winner_raw;
+            oc.fin_raw = as.fin_raw;
+            oc.penalised = as.penalised;
+            oc.refunds = as.refunds;
+            oc.winner = as.winner;
+        }
+    }
+}
+
 template <int N, bool IND, bool POLICY>
 __device__ __forceinline__ void warp_assist(const StepParams &p, const Env<N> &s, long long e, bool valid, int action,
                                             uint32_t policy_rnd, int lane, uint8_t *scratch, Assist &as) {
@@ -182,45 +277,7 @@ __device__ __forceinline__ void warp_assist(const StepParams &p, const Env<N> &s
         const int is_over = __shfl_sync(FULL, (int)over, L);
         if (is_over) {
             const int curL = __shfl_sync(FULL, cur, L);
-            uint32_t v[3];
-            row_cards(mine, v);  // hidden cards count at their true value (skyjo.py:488-493)
-            const int raw = score12(v);
-            const int ref = (int)sk_popc(row_flags(mine));
-            const int mn = __reduce_min_sync(FULL, act ? raw : 0x7FFFFFFF);
-            const int raw_sum = __reduce_add_sync(FULL, act ? raw : 0);
-            const int refunds = __reduce_add_sync(FULL, act ? ref : 0);
-            const int fin_raw = __shfl_sync(FULL, raw, curL);
-            const bool penalised = mn != fin_raw;  // skyjo.py:496
-            double sc = (double)raw;
-            if (penalised && lane == curL) sc = sk_dmul(sc, p.score_penalty);
-            double a[N];
-#pragma unroll
-            for (int q = 0; q < N; ++q) a[q] = __shfl_sync(FULL, sc, q);
-            const double mean = sk_ddiv(np_sum<N>(a), (double)N);  // skyjo_env.py:307-311
-            int winner = 0;
-            double best = a[0];
-#pragma unroll
-            for (int q = 1; q < N; ++q)
-                if (a[q] < best) {
-                    best = a[q];
-                    winner = q;
-                }
-            if (act) {
-                double r = sk_dadd(sk_dadd(-sc, mean), p.mean_reward);
-                if (p.reward_refunded != 0.0) r = sk_dadd(r, sk_dmul((double)ref, p.reward_refunded));
-                const long long eL = e - lane + L;
-                p.reward[eL * N + lane] = r;
-                p.final_score[eL * N + lane] = sc;
-            }
-            if (lane == L) {
-                as.scored = 1;
-                as.raw_sum = raw_sum;
-                as.winner_raw = mn;
-                as.fin_raw = fin_raw;
-                as.penalised = penalised ? 1 : 0;
-                as.refunds = refunds;
-                as.winner = winner;
-            }
+            warp_score_row<N>(p, mine, act, curL, e - lane + L, lane, lane == L, as);
         } else {
             // open table cards of my row, as histogram increments (skyjo.py:241-246 count_players_cards)
             uint64_t c = 0;
@@ -313,10 +370,14 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     uint32_t dirty_rows = 0, pf_new = PF_KEEP;
     int done_code = SKYJO_RUNNING;
     constexpr bool ASSIST = N >= SKYJO_ASSIST_MIN_N;
+    constexpr bool DEFER = !ASSIST && SKYJO_DEFER_SCORING != 0;
     Assist as;
     if (ASSIST) warp_assist<N, IND, POLICY>(p, s, e, valid, action, policy_rnd, lane, smem + (size_t)warp * 32 * D, as);
+    Outcome oc;
+    oc.scored = 0;
+    if (valid) oc = env_step<N, IND, POLICY, ASSIST, DEFER>(p, e, s, action, policy_rnd, &as);
+    if (DEFER) warp_score_deferred<N>(p, s, e, lane, smem + (size_t)warp * 32 * D, oc);
     if (valid) {
-        const Outcome oc = env_step<N, IND, POLICY, ASSIST>(p, e, s, action, policy_rnd, &as);
         dirty_rows = oc.dirty_rows;
         pf_new = oc.pf_new;
         done_code = oc.done_code;
@@ -451,10 +512,14 @@ __global__ void __launch_bounds__(TILE, ROLLOUT_MIN_CTAS(N))
         int act_class = -1, done_code = SKYJO_RUNNING;
         uint32_t pf_new = PF_KEEP;
         constexpr bool ASSIST = N >= SKYJO_ASSIST_MIN_N;
+        constexpr bool DEFER = !ASSIST && SKYJO_DEFER_SCORING != 0;
         Assist as;
         if (ASSIST) warp_assist<N, IND, true>(p, s, e, valid, 0, policy_rnd, lane, smem + (size_t)warp * 32 * D, as);
+        Outcome oc;
+        oc.scored = 0;
+        if (valid) oc = env_step<N, IND, true, ASSIST, DEFER>(p, e, s, 0, policy_rnd, &as);
+        if (DEFER) warp_score_deferred<N>(p, s, e, lane, smem + (size_t)warp * 32 * D, oc);
         if (valid) {
-            const Outcome oc = env_step<N, IND, true, ASSIST>(p, e, s, 0, policy_rnd, &as);
             dirty_all |= oc.dirty_rows;
             pf_new = oc.pf_new;
             done_code = oc.done_code;
