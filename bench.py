@@ -572,8 +572,8 @@ def run_policy_rollout(args, dev):
             "policy_kernel_us": k_us, "tflops_issued": flop_issued / (k_us * 1e-6) / 1e12,
             "tflops_useful": flop_useful / (k_us * 1e-6) / 1e12, "peak_bf16_tflops": peak_tf,
             "tensor_frac_issued": flop_issued / (k_us * 1e-6) / 1e12 / peak_tf,
-            "sfu_bound_us": B * 512 / (148 * 16 * 1.965e9) * 1e6,
-            "note": "bf16 operands, fp32 accumulation; 512 tanh per env on the SFUs (16 per clock per SM) bound the "
+            "sfu_bound_us": B * 512 / (148 * 8 * 1.965e9) * 1e6,
+            "note": "bf16 operands, fp32 accumulation; 512 tanh per env on the SFUs (MUFU.TANH: 8 per clock per SM) bound the "
                     "kernel before the tensor cores do (sfu_bound_us at 1965 MHz)"}
     env.check()
     assert ptr == (env.observations.data_ptr(), env.action_mask.data_ptr()), "obs / mask must be consumed in place"

@@ -106,10 +106,16 @@ class BatchedSkyjoEnv:
         self._observation_spaces = {a: obs_space for a in self.possible_agents}
         self._action_spaces = {a: Discrete(_lib.NUM_ACTIONS) for a in self.possible_agents}
         self._has_reset = False
+        self.stream = None
 
     # ---- plumbing ---------------------------------------------------------------------
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        # `stream` (a torch.cuda.Stream, default None = torch's current stream at the time of each call) pins every
+        # launch of this env -- and of a FusedPolicy built on it -- to one stream, so that two envs can be driven
+        # from one thread on two streams without a stream context per call.  Tensors handed in from other streams
+        # need the caller's own wait_stream / record_stream.
+        st = self.stream
+        return st.cuda_stream if st is not None else torch.cuda.current_stream(self.device).cuda_stream
 
     def __del__(self):
         try:
