@@ -113,7 +113,8 @@ class BatchedSkyjoEnv:
         # `stream` (a torch.cuda.Stream, default None = torch's current stream at the time of each call) pins every
         # launch of this env -- and of a FusedPolicy built on it -- to one stream, so that two envs can be driven
         # from one thread on two streams without a stream context per call.  Tensors handed in from other streams
-        # need the caller's own wait_stream / record_stream.
+        # need the caller's own wait_stream / record_stream, and buffers should be allocated up front (torch's
+        # caching allocator associates a block with the stream that was current when it was allocated).
         st = self.stream
         return st.cuda_stream if st is not None else torch.cuda.current_stream(self.device).cuda_stream
 
