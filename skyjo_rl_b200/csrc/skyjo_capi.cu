@@ -94,6 +94,18 @@ struct SkyjoHandle {
     bool ranges_ready;
     cudaStream_t range_stream[HOSTIO_MAX_CHUNKS];
     cudaEvent_t ev_fork, ev_join[HOSTIO_MAX_CHUNKS];
+    // skyjo_step_random(n) replayed from a CUDA graph (see step_random_ranges): one instantiated graph per
+    // (n, starting flag-array parity); t_dev = the device-resident lockstep counter its kernels read
+    struct StepGraph {
+        int n_steps, parity, seen;
+        long long launches;
+        cudaGraphExec_t exec;
+    };
+    std::vector<StepGraph> graphs;
+    bool graphs_enabled;
+    unsigned long long *t_dev, t_dev_val;
+    bool t_dev_valid;
+    cudaStream_t capture_stream;
     int obs_len;
     int pf_dist;  // L2 prefetch distance of the step kernel, in tiles
     // optional per-kernel event timing (skyjo_step_random_profile)
@@ -258,6 +270,11 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     h->deal_pending[0] = h->deal_pending[1] = false;
     h->deal_async_enabled = getenv("SKYJO_SYNC_DEAL") == nullptr;
     h->ranges_ready = false;
+    h->graphs_enabled = getenv("SKYJO_NO_GRAPH") == nullptr;
+    h->t_dev = nullptr;
+    h->capture_stream = nullptr;
+    h->t_dev_val = 0;
+    h->t_dev_valid = false;
     h->n_ranges = num_envs >= (1 << 18) ? 4 : 1;
     if (const char *g = getenv("SKYJO_RANGES")) h->n_ranges = atoi(g);  // experiment knob
     if (h->n_ranges < 1) h->n_ranges = 1;
@@ -350,7 +367,21 @@ static void hostio_release(SkyjoHandle *h) {
     h->hostio_ready = false;
 }
 
+// the instantiated step graphs bake the output pointers, the seed and the env ranges: dropped when one changes
+static void graphs_drop(SkyjoHandle *h) {
+    for (auto &g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
 int skyjo_destroy(SkyjoHandle *h) {
+    if (h && (!h->graphs.empty() || h->t_dev)) {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        graphs_drop(h);
+        cudaFree(h->t_dev);
+        if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+    }
     if (h && h->ranges_ready) {
         cudaSetDevice(h->device);
         for (int r = 0; r < HOSTIO_MAX_CHUNKS; ++r) {
@@ -387,6 +418,7 @@ int skyjo_bind_outputs(SkyjoHandle *h, const SkyjoOutputs *o) {
         return fail(SKYJO_E_INVALID, "all six output buffers are required");
     if (((uintptr_t)o->reward_dev & 7) || ((uintptr_t)o->final_score_dev & 7))
         return fail(SKYJO_E_INVALID, "reward / final_score must be 8-byte aligned");
+    graphs_drop(h);
     h->outs = *o;
     h->bulk_ok = (((uintptr_t)o->obs_dev & 15) == 0 && ((uintptr_t)o->action_mask_dev & 15) == 0) ? 1 : 0;
     h->bound = true;
@@ -549,6 +581,7 @@ int skyjo_seed(SkyjoHandle *h, uint64_t seed, void *stream) {
     // counters are zeroed, or the flagged envs restart at episode 1 / 2 instead of 0
     int rc = quiesce(h, (cudaStream_t)stream);
     if (rc) return rc;
+    graphs_drop(h);
     h->seed = seed;
     h->t = 0;
     CU(cudaMemsetAsync(h->st.episode, 0, (size_t)h->Bpad * 4, (cudaStream_t)stream));
@@ -611,22 +644,27 @@ int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *
     return step_once(h, actions_dev, action_dtype, false, (cudaStream_t)stream);
 }
 
-// The envs of a batch never interact, so a batch can be stepped as R independent env ranges, each
-// on its own stream: step kernel (tile sub-range) x n, with the range's flagged deal after every
-// window, all in stream order.  The GPU interleaves the ranges, so the launch ramp and tail of one
-// range's kernel are covered by the other ranges' CTAs (at 2^20 envs a lone full-batch launch
-// loses ~7 of 52 us to them), without any cross-kernel memory-ordering assumption.
-static int step_random_ranges(SkyjoHandle *h, int n_steps, cudaStream_t s) {
-    if (!h->ranges_ready) {
-        for (int r = 0; r < HOSTIO_MAX_CHUNKS; ++r) {
-            CU(cudaStreamCreateWithFlags(&h->range_stream[r], cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&h->ev_join[r], cudaEventDisableTiming));
-        }
-        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        h->ranges_ready = true;
-    }
-    int rc = quiesce(h, s);  // no window open, no deal pending on deal_stream
-    if (rc) return rc;
+__global__ void set_t_kernel(unsigned long long *t_dev, unsigned long long v) { *t_dev = v; }
+__global__ void advance_t_kernel(unsigned long long *t_dev, unsigned long long n) { *t_dev += n; }
+
+// number of refill deals n lockstep steps with the in-kernel policy end with (the last, shorter window included)
+static int windows_in(const SkyjoHandle *h, int n_steps) {
+    const int period = deal_period(h, true);
+    return (n_steps + period - 1) / period;
+}
+
+// The launches of step_random_ranges replay unchanged from call to call when (a) the lockstep counter comes from
+// device memory and (b) the call toggles the flag-array parity an even number of times: then one instantiated CUDA
+// graph per (n_steps, starting parity) stands for the ~4 n kernel launches and their fork / join events, and the
+// host side of a call shrinks from ~1 ms per 64 steps (3.7 us per launch; as long as the device takes at 2^18
+// envs, and what eight ranks sharing 32 cores stumble over) to one cudaGraphLaunch.
+static bool graph_eligible(const SkyjoHandle *h, int n_steps) {
+    return h->graphs_enabled && !h->profiling && n_steps >= 8 && (!h->cfg.auto_reset || windows_in(h, n_steps) % 2 == 0);
+}
+
+// enqueues the n_steps x ranges step launches and their flagged deals, forked from / joined back into `s`; with
+// `graph` the kernels take their lockstep counter as *t_dev + offset (the calls are being captured)
+static int enqueue_ranges(SkyjoHandle *h, int n_steps, cudaStream_t s, bool graph) {
     const int R = h->n_ranges;
     const long long per = align_up((h->B + R - 1) / R, ENV_PAD);
     long long b0[HOSTIO_MAX_CHUNKS], b1[HOSTIO_MAX_CHUNKS];
@@ -643,6 +681,10 @@ static int step_random_ranges(SkyjoHandle *h, int n_steps, cudaStream_t s) {
     int in_window = 0;
     for (int i = 0; i < n_steps; ++i) {
         StepParams p = make_params(h);
+        if (graph) {
+            p.t_base = h->t_dev;
+            p.t = (unsigned long long)i;
+        }
         for (int r = 0; r < nr; ++r) {
             p.tile_off = b0[r] / TILE;
             p.tiles = (b1[r] - b0[r] + TILE - 1) / TILE;
@@ -654,7 +696,7 @@ static int step_random_ranges(SkyjoHandle *h, int n_steps, cudaStream_t s) {
             in_window = 0;
             if (h->cfg.auto_reset) {
                 for (int r = 0; r < nr; ++r) {
-                    rc = launch_deal(h, 1, 1, nullptr, nullptr, h->range_stream[r], b0[r], b1[r]);
+                    int rc = launch_deal(h, 1, 1, nullptr, nullptr, h->range_stream[r], b0[r], b1[r]);
                     if (rc) return rc;
                 }
                 h->parity ^= 1;
@@ -669,12 +711,90 @@ static int step_random_ranges(SkyjoHandle *h, int n_steps, cudaStream_t s) {
     return SKYJO_OK;
 }
 
+// The envs of a batch never interact, so a batch can be stepped as R independent env ranges, each
+// on its own stream: step kernel (tile sub-range) x n, with the range's flagged deal after every
+// window, all in stream order.  The GPU interleaves the ranges, so the launch ramp and tail of one
+// range's kernel are covered by the other ranges' CTAs (at 2^20 envs a lone full-batch launch
+// loses ~7 of 52 us to them), without any cross-kernel memory-ordering assumption.
+static int step_random_ranges(SkyjoHandle *h, int n_steps, cudaStream_t s) {
+    if (!h->ranges_ready) {
+        for (int r = 0; r < HOSTIO_MAX_CHUNKS; ++r) {
+            CU(cudaStreamCreateWithFlags(&h->range_stream[r], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->ev_join[r], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        h->ranges_ready = true;
+    }
+    int rc = quiesce(h, s);  // no window open, no deal pending on deal_stream
+    if (rc) return rc;
+    if (!graph_eligible(h, n_steps)) return enqueue_ranges(h, n_steps, s, false);
+
+    // a call shape is captured the second time it is seen (capture + instantiation cost about two direct calls)
+    SkyjoHandle::StepGraph *g = nullptr;
+    for (auto &c : h->graphs)
+        if (c.n_steps == n_steps && c.parity == h->parity) g = &c;
+    if (!g) {
+        if (h->graphs.size() >= 16) {  // a caller cycling through many shapes: forget the oldest
+            if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec);
+            h->graphs.erase(h->graphs.begin());
+        }
+        h->graphs.push_back({n_steps, h->parity, 1, 0, nullptr});
+        return enqueue_ranges(h, n_steps, s, false);
+    }
+    if (!g->exec) {
+        if (!h->t_dev) CU(cudaMalloc(&h->t_dev, 8));
+        const unsigned long long t0 = h->t;
+        const long long l0 = h->launches;
+        const int parity0 = h->parity;
+        cudaGraph_t graph = nullptr;
+        // captured on a stream of the library's own (the caller's may be the legacy default stream, which cannot
+        // capture); the graph is launched into the caller's stream
+        if (!h->capture_stream) CU(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+        const cudaStream_t cs = h->capture_stream;
+        CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_ranges(h, n_steps, cs, true);
+        if (rc == SKYJO_OK) {
+            advance_t_kernel<<<1, 1, 0, cs>>>(h->t_dev, (unsigned long long)n_steps);
+            if (cudaGetLastError() != cudaSuccess) rc = SKYJO_E_CUDA;
+        }
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        // the capture ran the host bookkeeping of one call without executing anything: take it back
+        g->launches = h->launches - l0 + 1;
+        h->t = t0;
+        h->launches = l0;
+        h->parity = parity0;
+        h->st.needs_deal = h->flags_base + (size_t)h->parity * (size_t)h->Bpad;
+        cudaError_t ie = cudaErrorUnknown;
+        if (rc == SKYJO_OK && ce == cudaSuccess && graph) ie = cudaGraphInstantiate(&g->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {  // no graphs on this driver / in this context: the direct path from now on
+            cudaGetLastError();
+            g->exec = nullptr;
+            h->graphs_enabled = false;
+            return enqueue_ranges(h, n_steps, s, false);
+        }
+    }
+    if (!h->t_dev_valid || h->t_dev_val != h->t) {
+        set_t_kernel<<<1, 1, 0, s>>>(h->t_dev, h->t);
+        CU(cudaGetLastError());
+    }
+    CU(cudaGraphLaunch(g->exec, s));
+    h->t += (unsigned long long)n_steps;
+    h->t_dev_val = h->t;
+    h->t_dev_valid = true;
+    h->launches += g->launches;
+    return SKYJO_OK;
+}
+
 int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream) {
     if (!h || n_steps < 0) return fail(SKYJO_E_INVALID, "bad argument");
     if (!h->bound) return fail(SKYJO_E_NOT_BOUND, "call skyjo_bind_outputs first");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
-    if (h->n_ranges > 1 && !h->profiling && n_steps >= 2) return step_random_ranges(h, n_steps, s);
+    // one range: the graph pays where the loop is launch-bound (a 2^15-env step kernel takes about the 3.7 us its
+    // launch costs the host; at 2^16 the async refill deals of the loop below are worth more)
+    if (!h->profiling && n_steps >= 2 && (h->n_ranges > 1 || (h->B <= (1 << 15) && graph_eligible(h, n_steps))))
+        return step_random_ranges(h, n_steps, s);
     for (int i = 0; i < n_steps; ++i) {
         int rc = step_once(h, nullptr, 0, true, s);
         if (rc) return rc;
@@ -687,6 +807,7 @@ int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream) {
 
 int skyjo_set_env_ranges(SkyjoHandle *h, int n) {
     if (!h || n < 0 || n > HOSTIO_MAX_CHUNKS) return fail(SKYJO_E_INVALID, "env ranges must be 0 (default) .. 8");
+    graphs_drop(h);
     h->n_ranges = n > 0 ? n : (h->B >= (1 << 18) ? 4 : 1);
     return SKYJO_OK;
 }

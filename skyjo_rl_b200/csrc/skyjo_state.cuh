@@ -254,6 +254,9 @@ struct StepParams {
     int action_dtype;
     long long B, Bpad;
     unsigned long long first_env, seed, t;
+    // launches replayed from a CUDA graph (skyjo_step_random, skyjo_capi.cu): the lockstep counter of the replay's
+    // first step lives in device memory and `t` is the step's offset in the replay; null otherwise
+    const unsigned long long *t_base;
     double score_penalty, mean_reward, reward_refunded;
     int auto_reset, max_steps;
     int bulk_ok;  // obs / mask base pointers 16-byte aligned -> TMA bulk stores

@@ -356,8 +356,14 @@ __global__ void __launch_bounds__(TILE, STEP_MIN_CTAS(N)) step_kernel(const __gr
     }
     // the policy's random word depends only on (seed, env, t): drawn before the wait, so CTAs that
     // were scheduled early have work to do while the previous step's grid drains
+    // (t_base is only written between two replays of the graph this launch belongs to, never by a predecessor
+    // that may still be running under programmatic dependent launch)
     uint32_t policy_rnd = 0u;
-    if (POLICY) policy_rnd = policy_random(p.seed, p.first_env + (unsigned long long)e, p.t);
+    if (POLICY) {
+        unsigned long long t = p.t;
+        if (p.t_base) t += *p.t_base;
+        policy_rnd = policy_random(p.seed, p.first_env + (unsigned long long)e, t);
+    }
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
     Env<N> s;
