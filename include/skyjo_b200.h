@@ -177,7 +177,12 @@ int skyjo_seed(SkyjoHandle *h, uint64_t seed, void *stream);
  * _calc_final_rewards (skyjo_env.py:293-312), collect_observation (skyjo.py:148-199). */
 int skyjo_step(SkyjoHandle *h, const void *actions_dev, int action_dtype, void *stream);
 /* n_steps fused launches with the uniform legal policy (random_admissible_policy.py:26-28)
- * drawn in-kernel: the loop of sample_game.py:10-21. */
+ * drawn in-kernel: the loop of sample_game.py:10-21.  From the second call with the same n_steps
+ * (>= 8) the whole launch sequence of a call -- step kernels of every env range, refill deals, the
+ * fork / join between the range streams -- is replayed from an instantiated CUDA graph whose kernels
+ * read the lockstep counter from device memory: one cudaGraphLaunch instead of ~4 n kernel launches
+ * (0.025 instead of 0.97 ms of host time per 64 steps at 2^20 envs).  Same games bit for bit;
+ * env SKYJO_NO_GRAPH=1 keeps the direct launches.  Batches of one range use the graph up to 2^15 envs. */
 int skyjo_step_random(SkyjoHandle *h, int n_steps, void *stream);
 /* skyjo_step_random steps a batch as n independent env ranges, each on its own CUDA stream with its own
  * refill deals (games never interact; one range's launch ramp / tail is covered by the others' CTAs).
