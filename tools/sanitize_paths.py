@@ -60,8 +60,13 @@ def ranges_and_stats():
     env.reset()
     env.set_env_ranges(4)
     for _ in range(3):
-        env.step_random(70)          # two refill windows and a remainder per call, on four streams
+        env.step_random(70)          # two refill windows and a remainder per call, on four streams (direct launches)
         out = env.stats_allreduce_async(None)
+    for _ in range(4):
+        env.step_random(64)          # an even number of windows: captured into a CUDA graph on the second call, replayed after
+        out = env.stats_allreduce_async(None)
+    env.step_random(5)               # direct launches in between: the device-side lockstep counter is brought up to date
+    env.step_random(64)
     env.stats_allreduce_wait()
     torch.cuda.synchronize()
     assert int(out[0]) >= 0
