@@ -153,3 +153,50 @@ def test_external_action_path_matches_oracle_on_sampled_envs_at_scale(N, B, mode
     assert ended > len(ids) // 2 and illegal > 0, (ended, illegal)
     st = env.stats()
     assert st["illegal"] >= illegal and st["episodes"] > B // 2
+
+
+@pytest.mark.parametrize("N,B,ranges,mode", [(4, 5000, 4, "next_step"), (2, 3000, 1, True), (8, 2500, 3, "next_step")])
+def test_graph_replayed_calls_play_the_same_games_as_direct_launches(N, B, ranges, mode, monkeypatch):
+    """skyjo_step_random replays a call shape from a CUDA graph from its third occurrence on (seen, captured,
+    replayed; the kernels then read the lockstep counter from device memory).  An env created with SKYJO_NO_GRAPH=1
+    launches directly: both must publish identical buffers after every call of a sequence that mixes replayed
+    shapes, shapes that cannot be replayed (an odd number of refill windows), single steps, a reseed and a restored
+    checkpoint."""
+    import torch
+    from skyjo_rl_b200 import BatchedSkyjoEnv
+    monkeypatch.setenv("SKYJO_NO_GRAPH", "1")
+    direct = BatchedSkyjoEnv(num_envs=B, num_players=N, seed=4, device="cuda:0", auto_reset=mode)
+    monkeypatch.delenv("SKYJO_NO_GRAPH")
+    graph = BatchedSkyjoEnv(num_envs=B, num_players=N, seed=4, device="cuda:0", auto_reset=mode)
+    for e in (direct, graph):
+        e.set_env_ranges(ranges)
+        e.reset()
+
+    def same(tag):
+        for name in ("observations", "action_mask", "agent_selection", "done_code", "rewards"):
+            assert torch.equal(getattr(direct, name), getattr(graph, name)), (tag, name)
+        assert direct.step_count == graph.step_count
+
+    saved = None
+    for i, n in enumerate([64, 64, 64, 64, 5, 64, 16, 1, 64, 128, 128, 128, 64]):
+        direct.step_random(n)
+        graph.step_random(n)
+        same((i, n))
+        if i == 5:
+            saved = graph.state_dict()
+    assert direct.stats() == graph.stats()
+    graph.load_state_dict(saved)            # back to the state after call 5: the device counter is stale now
+    direct.load_state_dict(saved)
+    for n in (64, 64, 7, 64):
+        direct.step_random(n)
+        graph.step_random(n)
+        same(("restored", n))
+    for e in (direct, graph):
+        e.seed(99)                          # drops the graphs (the seed is baked into their kernel parameters)
+    for n in (64, 64, 64, 64):
+        direct.step_random(n)
+        graph.step_random(n)
+        same(("reseeded", n))
+    direct.check()
+    graph.check()
+    assert torch.equal(direct.state_dict()["state"], graph.state_dict()["state"])
