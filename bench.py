@@ -225,7 +225,8 @@ def workload_config(N, B, indirect, reset, world, args):
                           "counted; value = counted act() transitions / time)" if reset == "next_step" else ""),
         "num_players": N, "envs_per_gpu": B, "global_envs": B * world, "obs_len": D,
         "parallelism": f"env-sharded x{world}, no data-path collective; per GPU the batch is stepped as 4 "
-                       "independent env ranges on 4 CUDA streams",
+                       "independent env ranges on 4 CUDA streams; an iteration's launches are replayed from one CUDA graph "
+                       "(graph_replays counts them)",
         "l2": f"no flush: ~{per_step_mb:.0f} MB touched per launch vs {L2_MB:.0f} MB L2 (inputs larger than L2)",
         "preroll_steps": args.preroll,
     }
@@ -305,7 +306,7 @@ def measure_step_loop(cx, N, B, indirect, reset, K, W, preroll, seed, profile_st
         iteration()
     env.stats_allreduce_wait()
     env.clear_stats()
-    l0 = env.launch_count
+    l0, g0 = env.launch_count, env.graph_replay_count
     sampler = ClockSampler(cx.local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cx.barrier()
@@ -319,6 +320,7 @@ def measure_step_loop(cx, N, B, indirect, reset, K, W, preroll, seed, profile_st
     clocks = sampler.stop()
     ms = cx.max_over_ranks(ev0.elapsed_time(ev1))
     launches = env.launch_count - l0
+    replays = env.graph_replay_count - g0
     reduced = last[0].clone()        # the library's all-reduced vector of the last iteration = the whole region
     check = cx.sum_over_ranks(env.stats_tensor())
     assert torch.equal(reduced, check), "side-stream statistics all-reduce disagrees with torch.distributed.all_reduce"
@@ -357,7 +359,7 @@ def measure_step_loop(cx, N, B, indirect, reset, K, W, preroll, seed, profile_st
     env.check()
     rec = {"value": value, "unit": UNIT, "steps": K, "warmup": W, "ms_per_step": ms / K,
            "us_per_launch": 1e3 * ms / (K * L), "timed_region_s": ms * 1e-3, "env_steps_per_step": L,
-           "gpu_launches": launches, "counted_env_steps": counted, "counted_frac": counted / float(B * world * K * L),
+           "gpu_launches": launches, "graph_replays": replays, "counted_env_steps": counted, "counted_frac": counted / float(B * world * K * L),
            "roofline": roofline, "clocks": clocks,
            "episode_stats": {k: stats[k] for k in ("episodes", "episode_steps", "refunds", "reshuffles", "steps")}}
     if not keep_env:
@@ -465,7 +467,8 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "int8", "data": "synthetic",
             "config": workload_config(N, B, args.indirect, args.reset, world, args),
-            "clocks": main["clocks"], "e2e": e2e, "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
+            "clocks": main["clocks"], "e2e": e2e, "gpu_launches": main["gpu_launches"],
+            "graph_replays": main["graph_replays"], "roofline": main["roofline"],
             "cpu_baseline": cpu, "rollout": rollout, "env_steps_per_step": L, "us_per_launch": main["us_per_launch"],
             "timed_region_s": main["timed_region_s"], "counted_env_steps": main["counted_env_steps"],
             "counted_frac": main["counted_frac"], "other_reset_mode": other, "policy_rollout": policy_rollout,

@@ -330,6 +330,9 @@ int64_t skyjo_step_count(const SkyjoHandle *h);
 int skyjo_set_step_count(SkyjoHandle *h, int64_t t);
 /* kernels launched by this handle so far */
 int64_t skyjo_launch_count(const SkyjoHandle *h);
+/* calls of skyjo_step_random served by a CUDA-graph replay so far (their kernels are counted by
+ * skyjo_launch_count like directly launched ones) */
+int64_t skyjo_graph_replay_count(const SkyjoHandle *h);
 
 /* Host twins of the device RNG streams, so a CPU checker can be dealt identical games. */
 void skyjo_host_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -32,7 +32,7 @@ EXPORTS = [
     "skyjo_step", "skyjo_step_random", "skyjo_rollout_random", "skyjo_profile_begin", "skyjo_profile_end",
     "skyjo_step_random_profile", "skyjo_step_host", "skyjo_set_host_threads", "skyjo_observe", "skyjo_stats_device",
     "skyjo_stats_host", "skyjo_stats_clear", "skyjo_sample_actions", "skyjo_quiesce", "skyjo_export_debug", "skyjo_check", "skyjo_step_count",
-    "skyjo_set_step_count", "skyjo_launch_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
+    "skyjo_set_step_count", "skyjo_launch_count", "skyjo_graph_replay_count", "skyjo_host_philox4x32_10", "skyjo_host_deck", "skyjo_host_flips",
     "skyjo_host_policy", "skyjo_host_expand_packed", "skyjo_set_host_wire", "skyjo_host_wire_bytes",
     "skyjo_host_obs_record_bytes", "skyjo_host_pack_obs", "skyjo_host_expand_obs", "skyjo_stats_allreduce",
     "skyjo_host_reshuffle", "skyjo_set_env_ranges", "skyjo_stats_allreduce_async", "skyjo_stats_allreduce_wait",
@@ -153,6 +153,7 @@ def load():
         "skyjo_step_count": (i64, [vp]),
         "skyjo_set_step_count": (i32, [vp, i64]),
         "skyjo_launch_count": (i64, [vp]),
+        "skyjo_graph_replay_count": (i64, [vp]),
         "skyjo_host_philox4x32_10": (None, [vp, vp, vp]),
         "skyjo_host_deck": (None, [u64, u64, u32, vp]),
         "skyjo_host_flips": (None, [u64, u64, u32, i32, vp]),

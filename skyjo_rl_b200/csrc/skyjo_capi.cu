@@ -105,6 +105,7 @@ struct SkyjoHandle {
     bool graphs_enabled;
     unsigned long long *t_dev, t_dev_val;
     bool t_dev_valid;
+    long long graph_replays;
     cudaStream_t capture_stream;
     int obs_len;
     int pf_dist;  // L2 prefetch distance of the step kernel, in tiles
@@ -272,6 +273,7 @@ int skyjo_create(const SkyjoConfig *cfg, int device, int64_t num_envs, uint64_t 
     h->ranges_ready = false;
     h->graphs_enabled = getenv("SKYJO_NO_GRAPH") == nullptr;
     h->t_dev = nullptr;
+    h->graph_replays = 0;
     h->capture_stream = nullptr;
     h->t_dev_val = 0;
     h->t_dev_valid = false;
@@ -783,6 +785,7 @@ static int step_random_ranges(SkyjoHandle *h, int n_steps, cudaStream_t s) {
     h->t_dev_val = h->t;
     h->t_dev_valid = true;
     h->launches += g->launches;
+    h->graph_replays += 1;
     return SKYJO_OK;
 }
 
@@ -1491,6 +1494,7 @@ int skyjo_set_step_count(SkyjoHandle *h, int64_t t) {
     return SKYJO_OK;
 }
 int64_t skyjo_launch_count(const SkyjoHandle *h) { return h ? h->launches : -1; }
+int64_t skyjo_graph_replay_count(const SkyjoHandle *h) { return h ? h->graph_replays : -1; }
 
 // ---- host twins of the device RNG (same header, host compilation path) ---------------------
 void skyjo_host_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {

@@ -412,6 +412,11 @@ class BatchedSkyjoEnv:
     def launch_count(self):
         return int(self._L.skyjo_launch_count(self._h))
 
+    @property
+    def graph_replay_count(self):
+        """step_random calls served by a CUDA-graph replay so far"""
+        return int(self._L.skyjo_graph_replay_count(self._h))
+
     def export(self, env0=0, count=None):
         """SkyjoGame-shaped dump of envs [env0, env0+count) as a list of GameView."""
         count = self.num_envs - env0 if count is None else count
