@@ -18,7 +18,7 @@
 Prints every mismatch with its parameters and a final count.  Round-1 totals (no mismatch): reference 36 178 games
 (7.1 M steps, 65 872 reshuffles), reference-strategy 3 076 games (3.3 M steps, 13 402 reshuffles, 5 067 removals),
 hostsim 3 676 runs, strategy 3 836 games (N = 1 .. 12; 7.2 M steps, 94 966 reshuffles, 8 638 removals), gpu 45 runs.
-Round 2 (no mismatch): gpu-chunked 298 runs (48.6 M env-steps), gpu 418 runs."""
+Round 2 (no mismatch): gpu-chunked 501 runs (83.3 M env-steps; the last 203 with the graph-replayed calls), gpu 418 runs."""
 import importlib.util
 import os
 import sys
