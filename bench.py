@@ -349,7 +349,7 @@ def measure_step_loop(cx, N, B, indirect, reset, K, W, preroll, seed, profile_st
                 "algorithmic_bytes_per_env_step": bps, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                 "deal_kernel_share": prof["deal_ms"] / max(prof["deal_ms"] + prof["step_ms"], 1e-9),
                 "note": "kernel_us = mean duration of a full-batch step launch on one stream: CUDA events bracket every "
-                        "window of 8 back-to-back launches between two refill deals (no event between launches; the "
+                        "window of back-to-back launches between two refill deals (32 at four players) (no event between launches; the "
                         "deals, in stream order, are timed by their own pairs); the timed loop behind `value` steps "
                         "the batch as 4 env ranges on 4 streams, so that one range's launch ramp / tail is covered by "
                         "the others",

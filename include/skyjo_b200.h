@@ -198,7 +198,8 @@ typedef struct SkyjoRollout {
     void *done_dev;
 } SkyjoRollout;
 /* The same n_steps env-steps as skyjo_step_random (identical games, statistics and final state),
- * run as multi-step launches: each kernel advances its envs by up to 8 consecutive env-steps with
+ * run as multi-step launches: each kernel advances its envs by up to 32 consecutive env-steps
+ * (the refill window: 8 / 16 / 24 / 32 for 1 / 2 / 3 / >= 4 players) with
  * the state held in registers and stores what step t would have published -- the next agent's
  * observation, action mask, agent and done code -- into slice t of the time-major buffers (the
  * rollout storage a learner consumes, sample_game.py:10-21 unrolled in time).  The bound [B, ...]
@@ -209,7 +210,7 @@ int skyjo_rollout_random(SkyjoHandle *h, int n_steps, const SkyjoRollout *out, v
 /* CUDA-event timing of everything launched between begin and end on `stream` (summed device ms
  * and launch counts of step / rollout kernels and of deal kernels); end synchronises.  One event
  * pair brackets each deal or rollout launch, and each WINDOW of back-to-back single-step launches
- * (the up to 8 launches between two refill deals): an event between two ~45 us step kernels would
+ * (the up to 32 launches between two refill deals): an event between two ~45 us step kernels would
  * add ~5 us to each pair and break their programmatic dependent launch.  Measurement aid for
  * bench.py's roofline figure. */
 int skyjo_profile_begin(SkyjoHandle *h);

@@ -207,7 +207,7 @@ class BatchedSkyjoEnv:
 
     def rollout_random(self, n_steps, out=None):
         """The env-steps of step_random(n_steps) as multi-step launches (state in registers across
-        up to 8 steps per kernel); what each step publishes goes to slice t of time-major tensors
+        up to 32 steps per kernel); what each step publishes goes to slice t of time-major tensors
         {"observations": int8[T,B,D], "action_mask": int8[T,B,26], "agent_selection": int8[T,B],
         "done_code": uint8[T,B]} (allocated here unless `out` is given)."""
         assert self._has_reset, "reset() needs to be called before step"
