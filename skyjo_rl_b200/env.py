@@ -114,7 +114,10 @@ class BatchedSkyjoEnv:
         # launch of this env -- and of a FusedPolicy built on it -- to one stream, so that two envs can be driven
         # from one thread on two streams without a stream context per call.  Tensors handed in from other streams
         # need the caller's own wait_stream / record_stream, and buffers should be allocated up front (torch's
-        # caching allocator associates a block with the stream that was current when it was allocated).
+        # caching allocator associates a block with the stream that was current when it was allocated).  Methods
+        # that convert or allocate tensors themselves (reset_injected, step with host-side or mistyped actions,
+        # rollout_random / sample_actions without output buffers, stats, export) do that on torch's CURRENT
+        # stream: with a pinned stream call them under `with torch.cuda.stream(env.stream):`.
         st = self.stream
         return st.cuda_stream if st is not None else torch.cuda.current_stream(self.device).cuda_stream
 

@@ -120,7 +120,8 @@ class FusedPolicy:
               for m in lin for t in (m.weight, m.bias)]
         self._lib.check(self._L.skyjo_policy_pack(self.env.obs_len, n_out, *[w.data_ptr() for w in ws],
                                                   dst.data_ptr(), self.env._stream()))
-        torch.cuda.current_stream(self.env.device).synchronize()      # the fp32 copies die with this frame
+        st = self.env.stream if self.env.stream is not None else torch.cuda.current_stream(self.env.device)
+        st.synchronize()                                               # the fp32 copies die with this frame
 
     def repack(self):
         self._pack(self.policy.logits_net, 26, self._packed)
