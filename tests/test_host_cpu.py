@@ -405,4 +405,5 @@ def test_round2_entry_points_validate_their_arguments():
     assert L.skyjo_stats_allreduce_async(None, None, None, None) == 1 and L.skyjo_stats_allreduce_wait(None, None) == 1
     assert L.skyjo_set_env_ranges(None, 2) == 1 and L.skyjo_host_wire_share(None) == -1
     assert L.skyjo_set_host_wire(None, 2) == 1
+    assert L.skyjo_graph_replay_count(None) == -1 and L.skyjo_launch_count(None) == -1
     assert L.skyjo_host_simd_level() in (0, 2, 3)
