@@ -18,7 +18,10 @@
 Prints every mismatch with its parameters and a final count.  Round-1 totals (no mismatch): reference 36 178 games
 (7.1 M steps, 65 872 reshuffles), reference-strategy 3 076 games (3.3 M steps, 13 402 reshuffles, 5 067 removals),
 hostsim 3 676 runs, strategy 3 836 games (N = 1 .. 12; 7.2 M steps, 94 966 reshuffles, 8 638 removals), gpu 45 runs.
-Round 2 (no mismatch): gpu-chunked 501 runs (83.3 M env-steps; the last 203 with the graph-replayed calls), gpu 418 runs."""
+Round 2 (no mismatch): gpu-chunked 501 runs (83.3 M env-steps; the last 203 with the graph-replayed calls), gpu 418 runs.
+Round 2, CPU modes after the last refactor of skyjo_core.cuh (no mismatch): hostsim 1 054 runs, reference 16 605 games
+(3.3 M steps, 30 378 reshuffles), strategy 839 games (1.8 M steps, 28 674 reshuffles, 2 166 removals),
+reference-strategy 1 233 games (1.3 M steps, 5 343 reshuffles, 2 110 removals)."""
 import importlib.util
 import os
 import sys
